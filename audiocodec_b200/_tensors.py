@@ -1,0 +1,56 @@
+"""Tensor plumbing for the host-side classes: device memory, streams and DLPack hand-over via PyTorch.
+
+PyTorch is used for allocation and stream bookkeeping only; every computation goes through the C ABI.
+Foreign tensors (anything exposing __dlpack__, e.g. TensorFlow eager tensors) are viewed zero-copy and
+results are handed back in the caller's framework.
+"""
+
+import numpy as np
+import torch
+
+
+def normalise_compute_dtype(dtype, who):
+  """Accepts tf / torch / numpy dtypes or strings; only float32 compute is built."""
+  name = getattr(dtype, "name", None) or str(dtype)
+  name = name.replace("torch.", "").replace("<dtype: '", "").replace("'>", "")
+  if name in ("float32", "float", "f32") or dtype is np.float32:
+    return "float32"
+  if name in ("float64", "double", "bfloat16"):
+    raise NotImplementedError(f"{who}: compute_dtype {name} is accepted by the reference but only float32 kernels are built")
+  raise TypeError(f"compute_dtype of {who} should be float64, float32 or bfloat16 (got {dtype!r})")
+
+
+def normalise_precompute_dtype(dtype):
+  name = getattr(dtype, "name", None) or str(dtype)
+  name = name.replace("torch.", "").replace("<dtype: '", "").replace("'>", "")
+  if name in ("float64", "double") or dtype is np.float64:
+    return "float64"
+  if name in ("float32", "float") or dtype is np.float32:
+    return "float32"
+  raise TypeError(f"precompute_dtype must be float64 or float32 (got {dtype!r})")
+
+
+def adopt(x, name, dtype=torch.float32):
+  """Returns (torch view of x, function mapping a torch result back to x's framework)."""
+  back = lambda t: t  # noqa: E731
+  if not isinstance(x, torch.Tensor):
+    if not hasattr(x, "__dlpack__"):
+      raise TypeError(f"{name}: expected a device tensor (torch.Tensor or any object with __dlpack__), got {type(x)!r}")
+    module = type(x).__module__
+    x = torch.from_dlpack(x)
+    if module.startswith("tensorflow"):
+      def back(t):
+        import tensorflow as tf  # lazy: only when the caller is TensorFlow
+        return tf.experimental.dlpack.from_dlpack(torch.utils.dlpack.to_dlpack(t))
+  if x.dtype != dtype:
+    raise TypeError(f"{name}: dtype {x.dtype} does not match the compute dtype {dtype} (no implicit casting)")
+  if not x.is_cuda:
+    raise RuntimeError(f"{name}: tensor is on {x.device}; audiocodec_b200 only runs on CUDA devices (no CPU path)")
+  x = x.contiguous()
+  if x.data_ptr() % 16 != 0:
+    x = x.clone()
+  return x, back
+
+
+def stream_ptr(device):
+  return torch.cuda.current_stream(device).cuda_stream

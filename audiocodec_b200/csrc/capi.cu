@@ -1,0 +1,451 @@
+// C ABI (include/audiocodec_b200.h): plan objects, argument validation, DLPack unwrapping.
+#include "../../include/audiocodec_b200.h"
+
+#include "kernels.h"
+#include "tables.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+// ---- minimal DLPack v0.x ABI (struct layout of dlpack.h; only what is needed to read a tensor) ----------
+extern "C" {
+typedef enum { ac_kDLCPU = 1, ac_kDLCUDA = 2, ac_kDLCUDAHost = 3, ac_kDLCUDAManaged = 13 } ac_DLDeviceType;
+typedef struct { int32_t device_type; int32_t device_id; } ac_DLDevice;
+typedef struct { uint8_t code; uint8_t bits; uint16_t lanes; } ac_DLDataType;   // code: 0 int, 1 uint, 2 float
+typedef struct {
+  void* data;
+  ac_DLDevice device;
+  int32_t ndim;
+  ac_DLDataType dtype;
+  int64_t* shape;
+  int64_t* strides;   // in elements; NULL = compact row-major
+  uint64_t byte_offset;
+} ac_DLTensor;
+struct DLManagedTensor {
+  ac_DLTensor dl_tensor;
+  void* manager_ctx;
+  void (*deleter)(struct DLManagedTensor* self);
+};
+}
+
+namespace {
+
+thread_local char g_error[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t err, const char* what) {
+  return fail(AC_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+template <typename T>
+cudaError_t upload(const std::vector<T>& host, const T** dev, std::vector<void*>& owned) {
+  void* p = nullptr;
+  cudaError_t err = cudaMalloc(&p, std::max<size_t>(host.size(), 1) * sizeof(T));
+  if (err != cudaSuccess) return err;
+  owned.push_back(p);
+  if (!host.empty()) {
+    err = cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice);
+    if (err != cudaSuccess) return err;
+  }
+  *dev = static_cast<const T*>(p);
+  return cudaSuccess;
+}
+
+}  // namespace
+
+namespace ac {
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace ac
+
+struct ac_mdct_plan {
+  int device = 0;
+  ac::MdctDeviceTables tb;
+  std::vector<void*> owned;
+};
+
+struct ac_pa_plan {
+  int device = 0;
+  ac::PaDeviceTables tb;
+  ac::PaTables host;
+  std::vector<void*> owned;
+};
+
+namespace {
+
+void free_all(std::vector<void*>& owned) {
+  for (void* p : owned) cudaFree(p);
+  owned.clear();
+}
+
+int check_window(int window_type) {
+  return (window_type == AC_WINDOW_ONES || window_type == AC_WINDOW_SINE || window_type == AC_WINDOW_VORBIS) ? 0 : -1;
+}
+
+// validates a DLPack tensor and returns its data pointer (incl. byte_offset)
+int unwrap_dl(struct DLManagedTensor* m, const char* name, int ndim, uint8_t code, void** data, const int64_t** shape) {
+  if (m == nullptr) return fail(AC_ERR_INVALID, "%s: null DLManagedTensor", name);
+  const ac_DLTensor& t = m->dl_tensor;
+  if (t.device.device_type != ac_kDLCUDA && t.device.device_type != ac_kDLCUDAManaged)
+    return fail(AC_ERR_INVALID, "%s: tensor is not on a CUDA device (DLDeviceType %d); there is no CPU path", name,
+                t.device.device_type);
+  int dev = -1;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return cuda_fail(err, "cudaGetDevice");
+  if (t.device.device_id != dev)
+    return fail(AC_ERR_INVALID, "%s: tensor lives on cuda:%d but the current device is cuda:%d", name, t.device.device_id, dev);
+  if (t.dtype.code != code || t.dtype.bits != 32 || t.dtype.lanes != 1)
+    return fail(AC_ERR_INVALID, "%s: dtype must be %s32 (input dtype must equal compute dtype, no implicit cast)", name,
+                code == 2 ? "float" : "int");
+  if (t.ndim != ndim) return fail(AC_ERR_INVALID, "%s: expected rank %d, got %d", name, ndim, t.ndim);
+  if (t.strides != nullptr) {
+    int64_t expect = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+      if (t.shape[d] != 1 && t.strides[d] != expect) return fail(AC_ERR_INVALID, "%s: tensor must be C-contiguous", name);
+      expect *= t.shape[d];
+    }
+  }
+  *data = static_cast<char*>(t.data) + t.byte_offset;
+  *shape = t.shape;
+  return AC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ac_last_error(void) { return g_error; }
+int ac_abi_version(void) { return AC_ABI_VERSION; }
+int64_t ac_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------------------------ host-side tables
+int ac_mdct_tables_host(int filters_n, int window_type, int precompute_f32, double* fold, double* unfold) {
+  if (filters_n < 2 || (filters_n % 2) != 0)
+    return fail(AC_ERR_INVALID, "number of filters used in mdct transformation needs to be even (got %d)", filters_n);
+  if (check_window(window_type) != 0) return fail(AC_ERR_INVALID, "unknown window type %d", window_type);
+  const ac::MdctTables t = ac::build_mdct_tables(filters_n, window_type, precompute_f32 != 0);
+  if (fold != nullptr) std::memcpy(fold, t.fold.data(), t.fold.size() * sizeof(double));
+  if (unfold != nullptr) std::memcpy(unfold, t.unfold.data(), t.unfold.size() * sizeof(double));
+  return AC_OK;
+}
+
+int ac_pa_tables_host(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha, float* W, float* W_inv,
+                      float* quiet, float* spreading, double* scalars) {
+  if (!(sample_rate > 0) || filter_bands_n < 1 || bark_bands_n < 1 || !(alpha > 0))
+    return fail(AC_ERR_INVALID, "invalid psychoacoustic parameters (sample_rate %g, filter_bands_n %d, bark_bands_n %d, alpha %g)",
+                sample_rate, filter_bands_n, bark_bands_n, alpha);
+  const ac::PaTables t = ac::build_pa_tables(sample_rate, filter_bands_n, bark_bands_n, alpha);
+  const int n = t.n, nb = t.nb;
+  if (W != nullptr)
+    for (size_t i = 0; i < t.w.size(); ++i) W[i] = static_cast<float>(t.w[i]);
+  if (W_inv != nullptr)
+    for (size_t i = 0; i < t.w_inv.size(); ++i) W_inv[i] = static_cast<float>(t.w_inv[i]);
+  if (quiet != nullptr)
+    for (int i = 0; i < nb; ++i) quiet[i] = static_cast<float>(t.quiet[i]);
+  if (spreading != nullptr)
+    for (int i = 0; i < nb; ++i)
+      for (int j = 0; j < nb; ++j) spreading[i * nb + j] = static_cast<float>(t.spread_fn[nb - i + j]);
+  if (scalars != nullptr) {
+    scalars[0] = t.max_frequency;
+    scalars[1] = t.max_bark;
+    scalars[2] = t.bark_band_width;
+    scalars[3] = t.db_min;
+  }
+  (void)n;
+  return AC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ MDCT
+int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_mdct_plan** out) {
+  if (out == nullptr) return fail(AC_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (filters_n < 2 || (filters_n % 2) != 0)
+    return fail(AC_ERR_INVALID, "number of filters used in mdct transformation needs to be even (got %d)", filters_n);
+  if (check_window(window_type) != 0) return fail(AC_ERR_INVALID, "unknown window type %d", window_type);
+  const bool fast = ac::mdct_has_fast_path(filters_n);
+  if (!fast && filters_n > 8192)
+    return fail(AC_ERR_UNSUPPORTED, "filters_n = %d: only powers of two in [16, 4096] or any even value <= 8192 are built", filters_n);
+  ac_mdct_plan* plan = new (std::nothrow) ac_mdct_plan();
+  if (plan == nullptr) return fail(AC_ERR_ALLOC, "out of host memory");
+  cudaError_t err = cudaGetDevice(&plan->device);
+  if (err != cudaSuccess) {
+    delete plan;
+    return cuda_fail(err, "cudaGetDevice (no CUDA device? this library has no CPU path)");
+  }
+  const int n = filters_n, h = n / 2;
+  const ac::MdctTables t = ac::build_mdct_tables(n, window_type, precompute_f32 != 0);
+  const double pi = 3.14159265358979323846;
+  const double scale_fwd = 1.0 / (n * std::sqrt(2.0)), scale_inv = 2.0 * std::sqrt(2.0);
+  std::vector<float4> fold(h), unfold(h);
+  std::vector<float2> tw(h), twf(h), twi(h), roots(h);
+  for (int p = 0; p < h; ++p) {
+    fold[p] = make_float4((float)t.fold[4 * p], (float)t.fold[4 * p + 1], (float)t.fold[4 * p + 2], (float)t.fold[4 * p + 3]);
+    unfold[p] = make_float4((float)t.unfold[4 * p], (float)t.unfold[4 * p + 1], (float)t.unfold[4 * p + 2], (float)t.unfold[4 * p + 3]);
+    const double ang = -pi * (p + 0.125) / n;
+    tw[p] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+    twf[p] = make_float2((float)(std::cos(ang) * scale_fwd), (float)(std::sin(ang) * scale_fwd));
+    twi[p] = make_float2((float)(std::cos(ang) * scale_inv), (float)(std::sin(ang) * scale_inv));
+    const double ra = -2.0 * pi * p / h;
+    roots[p] = make_float2((float)std::cos(ra), (float)std::sin(ra));
+  }
+  std::vector<float> cos_table;
+  if (!fast) {
+    cos_table.resize(static_cast<size_t>(8) * n);
+    for (int m = 0; m < 8 * n; ++m) cos_table[m] = (float)std::cos(pi * m / (4.0 * n));
+  }
+  plan->tb.n = n;
+  plan->tb.scale_fwd = (float)scale_fwd;
+  plan->tb.scale_inv = (float)scale_inv;
+  if ((err = upload(fold, &plan->tb.fold, plan->owned)) != cudaSuccess ||
+      (err = upload(unfold, &plan->tb.unfold, plan->owned)) != cudaSuccess ||
+      (err = upload(tw, &plan->tb.tw_pre, plan->owned)) != cudaSuccess ||
+      (err = upload(twf, &plan->tb.tw_post_fwd, plan->owned)) != cudaSuccess ||
+      (err = upload(twi, &plan->tb.tw_post_inv, plan->owned)) != cudaSuccess ||
+      (err = upload(roots, &plan->tb.roots, plan->owned)) != cudaSuccess ||
+      (err = upload(cos_table, &plan->tb.cos_table, plan->owned)) != cudaSuccess) {
+    free_all(plan->owned);
+    delete plan;
+    return cuda_fail(err, "uploading MDCT tables");
+  }
+  *out = plan;
+  return AC_OK;
+}
+
+int ac_mdct_plan_destroy(ac_mdct_plan* plan) {
+  if (plan == nullptr) return AC_OK;
+  free_all(plan->owned);
+  delete plan;
+  return AC_OK;
+}
+
+static int check_common(const void* plan, int64_t batches, int64_t len, int channels) {
+  if (plan == nullptr) return fail(AC_ERR_INVALID, "plan is null");
+  if (batches < 0 || len < 0 || channels < 1) return fail(AC_ERR_INVALID, "negative size or channels < 1");
+  return AC_OK;
+}
+
+int ac_mdct_forward_f32(const ac_mdct_plan* plan, const float* x, float* y, int64_t batches, int64_t samples,
+                        int channels, void* stream) {
+  if (int rc = check_common(plan, batches, samples, channels)) return rc;
+  const int n = plan->tb.n;
+  if (samples % n != 0)
+    return fail(AC_ERR_INVALID, "samples_n (%lld) must be a multiple of filters_n (%d)", (long long)samples, n);
+  const int64_t blocks = samples / n;
+  if (blocks + 1 > 2147483647LL / 2) return fail(AC_ERR_INVALID, "too many blocks per batch row");
+  if (batches == 0) return AC_OK;
+  if (x == nullptr && samples > 0) return fail(AC_ERR_INVALID, "x is null");
+  if (y == nullptr) return fail(AC_ERR_INVALID, "y is null");
+  if (!aligned16(x) || !aligned16(y)) return fail(AC_ERR_INVALID, "x and y must be 16-byte aligned");
+  cudaError_t err = ac::mdct_forward(plan->tb, x, y, batches, blocks, channels, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "mdct_forward launch");
+}
+
+static int inverse_common(const ac_mdct_plan* plan, const float* y, const int32_t* q, const float* thr, float* x,
+                          int64_t batches, int64_t blocks, int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (blocks + 1 > 2147483647LL / 2) return fail(AC_ERR_INVALID, "too many blocks per batch row");
+  if (batches == 0) return AC_OK;
+  if (x == nullptr) return fail(AC_ERR_INVALID, "x is null");
+  if (blocks > 0) {
+    if (q == nullptr && y == nullptr) return fail(AC_ERR_INVALID, "y is null");
+    if (q != nullptr && thr == nullptr) return fail(AC_ERR_INVALID, "thr is null");
+  }
+  if (!aligned16(x) || !aligned16(y) || !aligned16(q) || !aligned16(thr))
+    return fail(AC_ERR_INVALID, "all tensors must be 16-byte aligned");
+  cudaError_t err = ac::mdct_inverse(plan->tb, y, q, thr, x, batches, blocks, channels, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "mdct_inverse launch");
+}
+
+int ac_mdct_inverse_f32(const ac_mdct_plan* plan, const float* y, float* x, int64_t batches, int64_t blocks,
+                        int channels, void* stream) {
+  return inverse_common(plan, y, nullptr, nullptr, x, batches, blocks, channels, stream);
+}
+
+int ac_mdct_inverse_dequant_f32(const ac_mdct_plan* plan, const int32_t* q, const float* thr, float* x,
+                                int64_t batches, int64_t blocks, int channels, void* stream) {
+  if (q == nullptr && blocks > 0 && batches > 0) return fail(AC_ERR_INVALID, "q is null");
+  return inverse_common(plan, nullptr, q, thr, x, batches, blocks, channels, stream);
+}
+
+// ------------------------------------------------------------------------------------- psychoacoustics
+int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha, ac_pa_plan** out) {
+  if (out == nullptr) return fail(AC_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (!(sample_rate > 0) || filter_bands_n < 1 || bark_bands_n < 1 || !(alpha > 0))
+    return fail(AC_ERR_INVALID, "invalid psychoacoustic parameters (sample_rate %g, filter_bands_n %d, bark_bands_n %d, alpha %g)",
+                sample_rate, filter_bands_n, bark_bands_n, alpha);
+  if (filter_bands_n > 16384 || bark_bands_n > 1024)
+    return fail(AC_ERR_UNSUPPORTED, "filter_bands_n <= 16384 and bark_bands_n <= 1024 are built");
+  ac_pa_plan* plan = new (std::nothrow) ac_pa_plan();
+  if (plan == nullptr) return fail(AC_ERR_ALLOC, "out of host memory");
+  cudaError_t err = cudaGetDevice(&plan->device);
+  if (err != cudaSuccess) {
+    delete plan;
+    return cuda_fail(err, "cudaGetDevice (no CUDA device? this library has no CPU path)");
+  }
+  plan->host = ac::build_pa_tables(sample_rate, filter_bands_n, bark_bands_n, alpha);
+  const ac::PaTables& t = plan->host;
+  ac::PaDeviceTables& d = plan->tb;
+  d.n = t.n;
+  d.nb = t.nb;
+  d.alpha = static_cast<float>(alpha);
+  d.neg_alpha = static_cast<float>(-alpha);
+  d.inv_alpha = static_cast<float>(1. / alpha);
+  d.eps = 1e-14f;
+  d.max_band_cnt = t.max_band_cnt;
+  d.max_filt_cnt = t.max_filt_cnt;
+  std::vector<float> quiet(t.quiet.begin(), t.quiet.end()), spread(t.spread_fn.begin(), t.spread_fn.end());
+  if ((err = upload(t.band_k0, &d.band_k0, plan->owned)) != cudaSuccess ||
+      (err = upload(t.band_cnt, &d.band_cnt, plan->owned)) != cudaSuccess ||
+      (err = upload(t.band_ptr, &d.band_ptr, plan->owned)) != cudaSuccess ||
+      (err = upload(t.band_w, &d.band_w, plan->owned)) != cudaSuccess ||
+      (err = upload(t.filt_b0, &d.filt_b0, plan->owned)) != cudaSuccess ||
+      (err = upload(t.filt_cnt, &d.filt_cnt, plan->owned)) != cudaSuccess ||
+      (err = upload(t.filt_ptr, &d.filt_ptr, plan->owned)) != cudaSuccess ||
+      (err = upload(t.filt_w, &d.filt_w, plan->owned)) != cudaSuccess ||
+      (err = upload(quiet, &d.quiet, plan->owned)) != cudaSuccess ||
+      (err = upload(spread, &d.spread_fn, plan->owned)) != cudaSuccess ||
+      (err = upload(t.lin, &d.lin, plan->owned)) != cudaSuccess) {
+    free_all(plan->owned);
+    delete plan;
+    return cuda_fail(err, "uploading psychoacoustic tables");
+  }
+  *out = plan;
+  return AC_OK;
+}
+
+int ac_pa_plan_destroy(ac_pa_plan* plan) {
+  if (plan == nullptr) return AC_OK;
+  free_all(plan->owned);
+  delete plan;
+  return AC_OK;
+}
+
+int ac_pa_tonality_f32(const ac_pa_plan* plan, const float* y, float* ton, int64_t batches, int64_t blocks,
+                       int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (batches * blocks == 0) return AC_OK;
+  if (y == nullptr || ton == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::pa_tonality(plan->tb, y, ton, batches * blocks, channels, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_tonality launch");
+}
+
+int ac_pa_threshold_f32(const ac_pa_plan* plan, const float* y, const float* ton, float drown, float* thr,
+                        int64_t batches, int64_t blocks, int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (batches * blocks == 0) return AC_OK;
+  if (y == nullptr || thr == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::pa_threshold(plan->tb, y, ton, drown, 1.0f, thr, nullptr, batches * blocks, channels,
+                                     static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_threshold launch");
+}
+
+int ac_pa_encode_f32(const ac_pa_plan* plan, const float* y, float drown, float thr_scale, float* thr_out, int32_t* q,
+                     int64_t batches, int64_t blocks, int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (!(thr_scale > 0.f)) return fail(AC_ERR_INVALID, "thr_scale must be positive");
+  if (batches * blocks == 0) return AC_OK;
+  if (y == nullptr || q == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::pa_threshold(plan->tb, y, nullptr, drown, thr_scale, thr_out, q, batches * blocks, channels,
+                                     static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_encode launch");
+}
+
+int ac_pa_add_noise_f32(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, void* stream) {
+  if (n < 0) return fail(AC_ERR_INVALID, "negative size");
+  if (n == 0) return AC_OK;
+  if (y == nullptr || thr == nullptr || out == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::add_noise(y, thr, out, n, seed, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "add_noise launch");
+}
+
+int ac_quantize_f32(const float* y, const float* thr, int32_t* q, int64_t n, void* stream) {
+  if (n < 0) return fail(AC_ERR_INVALID, "negative size");
+  if (n == 0) return AC_OK;
+  if (y == nullptr || thr == nullptr || q == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::quantize(y, thr, q, n, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "quantize launch");
+}
+
+int ac_dequantize_f32(const int32_t* q, const float* thr, float* y, int64_t n, void* stream) {
+  if (n < 0) return fail(AC_ERR_INVALID, "negative size");
+  if (n == 0) return AC_OK;
+  if (y == nullptr || thr == nullptr || q == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::dequantize(q, thr, y, n, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "dequantize launch");
+}
+
+// ---------------------------------------------------------------------------------------------- DLPack
+int ac_mdct_forward_dl(const ac_mdct_plan* plan, struct DLManagedTensor* x, struct DLManagedTensor* y, void* stream) {
+  if (plan == nullptr) return fail(AC_ERR_INVALID, "plan is null");
+  void *xd, *yd;
+  const int64_t *xs, *ys;
+  if (int rc = unwrap_dl(x, "x", 3, 2, &xd, &xs)) return rc;
+  if (int rc = unwrap_dl(y, "y", 4, 2, &yd, &ys)) return rc;
+  const int n = plan->tb.n;
+  if (xs[1] % n != 0)
+    return fail(AC_ERR_INVALID, "samples_n (%lld) must be a multiple of filters_n (%d)", (long long)xs[1], n);
+  if (ys[0] != xs[0] || ys[1] != xs[1] / n + 1 || ys[2] != n || ys[3] != xs[2])
+    return fail(AC_ERR_INVALID, "y must have shape [batches, samples / filters_n + 1, filters_n, channels]");
+  return ac_mdct_forward_f32(plan, static_cast<const float*>(xd), static_cast<float*>(yd), xs[0], xs[1], (int)xs[2], stream);
+}
+
+int ac_mdct_inverse_dl(const ac_mdct_plan* plan, struct DLManagedTensor* y, struct DLManagedTensor* x, void* stream) {
+  if (plan == nullptr) return fail(AC_ERR_INVALID, "plan is null");
+  void *xd, *yd;
+  const int64_t *xs, *ys;
+  if (int rc = unwrap_dl(y, "mdct_amplitudes", 4, 2, &yd, &ys)) return rc;
+  if (int rc = unwrap_dl(x, "x", 3, 2, &xd, &xs)) return rc;
+  const int n = plan->tb.n;
+  if (ys[2] != n) return fail(AC_ERR_INVALID, "mdct_amplitudes.shape[2] (%lld) != filters_n (%d)", (long long)ys[2], n);
+  if (xs[0] != ys[0] || xs[1] != (ys[1] + 1) * n || xs[2] != ys[3])
+    return fail(AC_ERR_INVALID, "x must have shape [batches, (blocks + 1) * filters_n, channels]");
+  return ac_mdct_inverse_f32(plan, static_cast<const float*>(yd), static_cast<float*>(xd), ys[0], ys[1], (int)ys[3], stream);
+}
+
+int ac_pa_tonality_dl(const ac_pa_plan* plan, struct DLManagedTensor* y, struct DLManagedTensor* ton, void* stream) {
+  if (plan == nullptr) return fail(AC_ERR_INVALID, "plan is null");
+  void *yd, *td;
+  const int64_t *ys, *ts;
+  if (int rc = unwrap_dl(y, "mdct_amplitudes", 4, 2, &yd, &ys)) return rc;
+  if (int rc = unwrap_dl(ton, "tonality", 4, 2, &td, &ts)) return rc;
+  if (ys[2] != plan->tb.n) return fail(AC_ERR_INVALID, "mdct_amplitudes.shape[2] != filter_bands_n");
+  if (ts[0] != ys[0] || ts[1] != ys[1] || ts[2] != 1 || ts[3] != ys[3])
+    return fail(AC_ERR_INVALID, "tonality must have shape [batches, blocks, 1, channels]");
+  return ac_pa_tonality_f32(plan, static_cast<const float*>(yd), static_cast<float*>(td), ys[0], ys[1], (int)ys[3], stream);
+}
+
+int ac_pa_threshold_dl(const ac_pa_plan* plan, struct DLManagedTensor* y, struct DLManagedTensor* ton_or_null, float drown,
+                       struct DLManagedTensor* thr, void* stream) {
+  if (plan == nullptr) return fail(AC_ERR_INVALID, "plan is null");
+  void *yd, *td = nullptr, *hd;
+  const int64_t *ys, *ts, *hs;
+  if (int rc = unwrap_dl(y, "mdct_amplitudes", 4, 2, &yd, &ys)) return rc;
+  if (int rc = unwrap_dl(thr, "threshold", 4, 2, &hd, &hs)) return rc;
+  if (ys[2] != plan->tb.n) return fail(AC_ERR_INVALID, "mdct_amplitudes.shape[2] != filter_bands_n");
+  for (int d = 0; d < 4; ++d)
+    if (hs[d] != ys[d]) return fail(AC_ERR_INVALID, "threshold must have the shape of mdct_amplitudes");
+  if (ton_or_null != nullptr) {
+    if (int rc = unwrap_dl(ton_or_null, "tonality_per_block", 4, 2, &td, &ts)) return rc;
+    if (ts[0] != ys[0] || ts[1] != ys[1] || ts[2] != 1 || ts[3] != ys[3])
+      return fail(AC_ERR_INVALID, "tonality_per_block must have shape [batches, blocks, 1, channels]");
+  }
+  return ac_pa_threshold_f32(plan, static_cast<const float*>(yd), static_cast<const float*>(td), drown,
+                             static_cast<float*>(hd), ys[0], ys[1], (int)ys[3], stream);
+}
+
+}  // extern "C"

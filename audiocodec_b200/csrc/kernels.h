@@ -1,0 +1,64 @@
+// Internal C++ interface between the C ABI (capi.cu) and the kernel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace ac {
+
+// Device-resident MDCT tables (all fp32, built in float64 on the host; tables.h documents the entries).
+struct MdctDeviceTables {
+  int n = 0;
+  float scale_fwd = 0.f;             // 1 / (N sqrt 2)  = (1 / sqrt(4N)) * sqrt(2 / N)   (mdctransformer.py:125, :314)
+  float scale_inv = 0.f;             // 2 sqrt 2        = sqrt(4N) * sqrt(2 / N)         (mdctransformer.py:145, :314)
+  const float4* fold = nullptr;      // [N/2]
+  const float4* unfold = nullptr;    // [N/2]
+  const float2* tw_pre = nullptr;    // [N/2]  exp(-i pi (j + 1/8) / N)
+  const float2* tw_post_fwd = nullptr;   // tw_pre * scale_fwd
+  const float2* tw_post_inv = nullptr;   // tw_pre * scale_inv
+  const float2* roots = nullptr;     // [N/2]  exp(-2 pi i j / (N/2))
+  const float* cos_table = nullptr;  // [8N]   cos(pi m / (4N)), generic-N path only
+};
+
+// Device-resident psychoacoustic tables (psychoacoustic.py:52-69, sparse forms from tables.h).
+struct PaDeviceTables {
+  int n = 0, nb = 0;
+  float alpha = 0.f;        // fp32(alpha), exponent of the non-linear superposition (psychoacoustic.py:206)
+  float neg_alpha = 0.f;    // fp32(-alpha)                                           (psychoacoustic.py:197)
+  float inv_alpha = 0.f;    // fp32(1 / alpha)                                        (psychoacoustic.py:208)
+  float eps = 1e-14f;       // _INTENSITY_EPS                                         (psychoacoustic.py:56)
+  int max_band_cnt = 0, max_filt_cnt = 0;
+  const int32_t* band_k0 = nullptr;
+  const int32_t* band_cnt = nullptr;
+  const int32_t* band_ptr = nullptr;
+  const float* band_w = nullptr;
+  const int32_t* filt_b0 = nullptr;
+  const int32_t* filt_cnt = nullptr;
+  const int32_t* filt_ptr = nullptr;
+  const float* filt_w = nullptr;
+  const float* quiet = nullptr;       // [nb]
+  const float* spread_fn = nullptr;   // [2 nb]
+  const float* lin = nullptr;         // [nb]
+};
+
+void count_launch();
+
+bool mdct_has_fast_path(int n);
+cudaError_t mdct_forward(const MdctDeviceTables& tb, const float* x, float* y, int64_t batches, int64_t blocks_n,
+                         int channels, cudaStream_t stream);
+// q == nullptr: plain inverse of y.  q != nullptr: inverse of q * thr (y ignored).
+cudaError_t mdct_inverse(const MdctDeviceTables& tb, const float* y, const int32_t* q, const float* thr, float* x,
+                         int64_t batches, int64_t frames_n, int channels, cudaStream_t stream);
+
+cudaError_t pa_tonality(const PaDeviceTables& tb, const float* y, float* ton, int64_t rows, int channels,
+                        cudaStream_t stream);
+// thr_out and q_out may each be null (not both).  ton_in may be null (tonality computed internally).
+cudaError_t pa_threshold(const PaDeviceTables& tb, const float* y, const float* ton_in, float drown, float thr_scale,
+                         float* thr_out, int32_t* q_out, int64_t rows, int channels, cudaStream_t stream);
+
+cudaError_t quantize(const float* y, const float* thr, int32_t* q, int64_t n, cudaStream_t stream);
+cudaError_t dequantize(const int32_t* q, const float* thr, float* y, int64_t n, cudaStream_t stream);
+cudaError_t add_noise(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, cudaStream_t stream);
+
+}  // namespace ac

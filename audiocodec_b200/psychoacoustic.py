@@ -1,0 +1,188 @@
+"""PsychoacousticModel: drop-in for /root/reference/audiocodec/psychoacoustic.py (class at :13-339).
+
+Same constructor keywords, attributes, method names and tensor layouts as the reference; tonality, the
+global masking threshold and the (build-defined) quantiser run as sm_100a kernels behind the C ABI.
+"""
+
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _capi
+from ._tensors import adopt, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr
+
+
+class PsychoacousticModel:
+  def __init__(self, sample_rate, filter_bands_n=1024, bark_bands_n=64, alpha=0.6,
+               compute_dtype='float32', precompute_dtype='float64'):
+    """Same arguments as the reference (psychoacoustic.py:14-15).
+
+    :raises TypeError: compute_dtype outside {float64, float32, bfloat16} (:42-43)
+    :raises NotImplementedError: float64 / bfloat16 compute (only float32 kernels are built)
+    """
+    self.alpha = alpha
+    self.sample_rate = sample_rate
+    self.bark_bands_n = int(bark_bands_n)
+    self.filter_bands_n = int(filter_bands_n)
+    self.compute_dtype = normalise_compute_dtype(compute_dtype, "PsychoacousticModel")
+    if normalise_precompute_dtype(precompute_dtype) != "float64":
+      raise NotImplementedError("PsychoacousticModel tables are precomputed in float64")
+
+    self._dB_MAX = 120.0                     # (:52)
+    self._INTENSITY_EPS = 1e-14              # (:56)
+
+    n, nb = self.filter_bands_n, self.bark_bands_n
+    w = np.empty((n, nb), dtype=np.float32)
+    w_inv = np.empty((nb, n), dtype=np.float32)
+    quiet = np.empty(nb, dtype=np.float32)
+    spreading = np.empty((nb, nb), dtype=np.float32)
+    scalars = np.empty(4, dtype=np.float64)
+    fp = ctypes.POINTER(ctypes.c_float)
+    _capi.check(_capi.lib().ac_pa_tables_host(
+      float(sample_rate), n, nb, float(alpha), w.ctypes.data_as(fp), w_inv.ctypes.data_as(fp),
+      quiet.ctypes.data_as(fp), spreading.ctypes.data_as(fp), scalars.ctypes.data_as(ctypes.POINTER(ctypes.c_double))))
+    self.max_frequency, self.max_bark, self.bark_band_width, self._dB_MIN = (float(v) for v in scalars)
+    self.W = torch.from_numpy(w)                                                   # [N, nb]      (:66)
+    self.W_inv = torch.from_numpy(w_inv)                                           # [nb, N]      (:67)
+    self.quiet_threshold_intensity = torch.from_numpy(quiet).reshape(1, 1, nb, 1)  # (:68)
+    self.spreading_matrix = torch.from_numpy(spreading)                            # [nb, nb]     (:69)
+    self._plans = {}
+
+  # ---- plans ------------------------------------------------------------------------------------------
+  def _plan(self, device):
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    plan = self._plans.get(index)
+    if plan is None:
+      handle = ctypes.c_void_p()
+      with torch.cuda.device(index):
+        _capi.check(_capi.lib().ac_pa_plan_create(float(self.sample_rate), self.filter_bands_n, self.bark_bands_n,
+                                                  float(self.alpha), ctypes.byref(handle)))
+      plan = self._plans[index] = handle
+    return plan
+
+  def __del__(self):
+    for handle in getattr(self, "_plans", {}).values():
+      try:
+        _capi.lib().ac_pa_plan_destroy(handle)
+      except Exception:
+        pass
+
+  def _check_amplitudes(self, a, name="mdct_amplitudes"):
+    if a.dim() != 4 or a.shape[2] != self.filter_bands_n:
+      raise ValueError(f"{name} must be [batches_n, blocks_n, {self.filter_bands_n}, channels_n], got {tuple(a.shape)}")
+
+  # ---- utilities (thin element-wise helpers; not part of the accelerated path) -------------------------
+  def amplitude_to_dB(self, mdct_amplitude):
+    """psychoacoustic.py:71-85."""
+    a = torch.as_tensor(mdct_amplitude, dtype=torch.float32)
+    return 10. * torch.log(torch.clamp_min(a ** 2.0, self._INTENSITY_EPS)) / math.log(10.) + self._dB_MAX
+
+  def amplitude_to_dB_norm(self, mdct_amplitude):
+    """psychoacoustic.py:87-100."""
+    return (self.amplitude_to_dB(mdct_amplitude) - self._dB_MIN) / (self._dB_MAX - self._dB_MIN)
+
+  @staticmethod
+  def freq2bark(frequencies):
+    """Empirical Bark scale (psychoacoustic.py:333-335)."""
+    return 6. * np.arcsinh(np.asarray(frequencies, dtype=np.float64) / 600.)
+
+  @staticmethod
+  def bark2freq(bark_band):
+    """Empirical Bark scale (psychoacoustic.py:337-339)."""
+    return 600. * np.sinh(np.asarray(bark_band, dtype=np.float64) / 6.)
+
+  # ---- data path --------------------------------------------------------------------------------------
+  def tonality(self, mdct_amplitudes):
+    """Spectral-flatness tonality, 0 (noise) .. 1 (tonal) (psychoacoustic.py:102-120).
+
+    :param mdct_amplitudes: [batches_n, blocks_n, filter_bands_n, channels_n], float32, CUDA
+    :return:                [batches_n, blocks_n, 1, channels_n]
+    """
+    a, back = adopt(mdct_amplitudes, "mdct_amplitudes")
+    self._check_amplitudes(a)
+    b, m, _, c = a.shape
+    ton = torch.empty((b, m, 1, c), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+      _capi.check(_capi.lib().ac_pa_tonality_f32(self._plan(a.device), a.data_ptr(), ton.data_ptr(), b, m, c,
+                                                 stream_ptr(a.device)))
+    return back(ton)
+
+  def global_masking_threshold(self, mdct_amplitudes, tonality_per_block, drown=0.0):
+    """Masking threshold amplitude per filter band (psychoacoustic.py:122-148).
+
+    :param tonality_per_block: [batches_n, blocks_n, 1, channels_n]; pass None to fuse the tonality of
+                               mdct_amplitudes into the same kernel (extension over the reference)
+    :param drown:              0..1, python float
+    :return:                   [batches_n, blocks_n, filter_bands_n, channels_n], never below 1e-7
+    """
+    a, back = adopt(mdct_amplitudes, "mdct_amplitudes")
+    self._check_amplitudes(a)
+    b, m, _, c = a.shape
+    ton_ptr = None
+    if tonality_per_block is not None:
+      ton, _ = adopt(tonality_per_block, "tonality_per_block")
+      if tuple(ton.shape) != (b, m, 1, c):
+        raise ValueError(f"tonality_per_block must be [{b}, {m}, 1, {c}], got {tuple(ton.shape)}")
+      ton_ptr = ton.data_ptr()
+    thr = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+      _capi.check(_capi.lib().ac_pa_threshold_f32(self._plan(a.device), a.data_ptr(), ton_ptr, float(drown),
+                                                  thr.data_ptr(), b, m, c, stream_ptr(a.device)))
+    return back(thr)
+
+  def add_noise(self, mdct_amplitudes, masking_threshold, seed=None):
+    """mdct_amplitudes + masking_threshold * N(0, 1/6) (psychoacoustic.py:150-167), Philox counter RNG."""
+    a, back = adopt(mdct_amplitudes, "mdct_amplitudes")
+    thr, _ = adopt(masking_threshold, "masking_threshold")
+    if a.shape != thr.shape:
+      raise ValueError("masking_threshold must have the shape of mdct_amplitudes")
+    if seed is None:
+      seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+    out = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+      _capi.check(_capi.lib().ac_pa_add_noise_f32(a.data_ptr(), thr.data_ptr(), out.data_ptr(), a.numel(),
+                                                  int(seed), stream_ptr(a.device)))
+    return back(out)
+
+  # ---- quantiser (build-defined: the reference has none) ---------------------------
+  def quantize(self, mdct_amplitudes, masking_threshold):
+    """q = rint(A / thr), int32 (IEEE divide, round-half-even)."""
+    a, _ = adopt(mdct_amplitudes, "mdct_amplitudes")
+    thr, _ = adopt(masking_threshold, "masking_threshold")
+    if a.shape != thr.shape:
+      raise ValueError("masking_threshold must have the shape of mdct_amplitudes")
+    q = torch.empty(a.shape, dtype=torch.int32, device=a.device)
+    with torch.cuda.device(a.device):
+      _capi.check(_capi.lib().ac_quantize_f32(a.data_ptr(), thr.data_ptr(), q.data_ptr(), a.numel(),
+                                              stream_ptr(a.device)))
+    return q
+
+  def dequantize(self, q, masking_threshold):
+    """A_hat = q * thr."""
+    q, _ = adopt(q, "q", dtype=torch.int32)
+    thr, back = adopt(masking_threshold, "masking_threshold")
+    if q.shape != thr.shape:
+      raise ValueError("masking_threshold must have the shape of q")
+    out = torch.empty_like(thr)
+    with torch.cuda.device(q.device):
+      _capi.check(_capi.lib().ac_dequantize_f32(q.data_ptr(), thr.data_ptr(), out.data_ptr(), q.numel(),
+                                                stream_ptr(q.device)))
+    return back(out)
+
+  def encode(self, mdct_amplitudes, drown=0.0, thr_scale=1.0, return_threshold=True):
+    """Encoder fusion: tonality -> threshold -> q = rint(A / (thr_scale * thr)) in one pass over A.
+
+    :return: (q int32, step float32) with step = thr_scale * threshold, or q alone.
+    """
+    a, _ = adopt(mdct_amplitudes, "mdct_amplitudes")
+    self._check_amplitudes(a)
+    b, m, _, c = a.shape
+    q = torch.empty(a.shape, dtype=torch.int32, device=a.device)
+    thr = torch.empty_like(a) if return_threshold else None
+    with torch.cuda.device(a.device):
+      _capi.check(_capi.lib().ac_pa_encode_f32(self._plan(a.device), a.data_ptr(), float(drown), float(thr_scale),
+                                               thr.data_ptr() if thr is not None else None, q.data_ptr(), b, m, c,
+                                               stream_ptr(a.device)))
+    return (q, thr) if return_threshold else q

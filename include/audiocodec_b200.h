@@ -1,0 +1,137 @@
+/* audiocodec_b200 — C ABI of the B200-native audiocodec hot path.
+ *
+ * The reference (korneelvdbroek/audiocodec, /root/reference) has no FFI layer: its boundary is two Python
+ * classes whose methods dispatch TensorFlow ops.  This header is the boundary a binding would target
+ * instead; each entry point names the reference interface it replaces (file:line under
+ * /root/reference/audiocodec/).  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types; every function returns an ac_status (0 = OK,
+ *     negative = error) and records a thread-local message retrievable with ac_last_error();
+ *   - the library never allocates caller-visible buffers and never synchronises: all device work is
+ *     enqueued on the caller's cudaStream_t (passed as void*; NULL = legacy default stream);
+ *   - data pointers are DEVICE pointers on the current CUDA device, fp32, C-contiguous, 16-byte aligned;
+ *     layouts are the reference's channels-last ones:  signal x [B, S, C],  amplitudes Y [B, M, N, C],
+ *     tonality [B, M, 1, C];
+ *   - plans are immutable after creation (device tables only) and may be shared between threads/streams
+ *     of the device they were created on;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     AC_ERR_CUDA.  Only the *_host table builders run without a GPU.
+ */
+#ifndef AUDIOCODEC_B200_H_
+#define AUDIOCODEC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define AC_ABI_VERSION 1
+
+typedef enum ac_status {
+  AC_OK = 0,
+  AC_ERR_INVALID = -1,      /* bad argument (shape, alignment, null pointer, odd filters_n, ...) */
+  AC_ERR_CUDA = -2,         /* CUDA runtime error (message carries cudaGetErrorString) */
+  AC_ERR_UNSUPPORTED = -3,  /* valid in the reference but not built here (e.g. bf16 compute) */
+  AC_ERR_ALLOC = -4
+} ac_status;
+
+typedef enum ac_window {     /* mdctransformer.py:199-211 */
+  AC_WINDOW_ONES = 0,        /* any string other than 'sine'/'vorbis' */
+  AC_WINDOW_SINE = 1,
+  AC_WINDOW_VORBIS = 2
+} ac_window;
+
+typedef struct ac_mdct_plan ac_mdct_plan;
+typedef struct ac_pa_plan ac_pa_plan;
+struct DLManagedTensor;      /* dlpack.h, DLPack v0.x ABI (the capsule named "dltensor") */
+
+/* ---------------------------------------------------------------------------------------- library */
+const char* ac_last_error(void);
+int ac_abi_version(void);
+/* Number of launches of this library's own kernels since load (all plans, this process). */
+int64_t ac_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------- host-side table builders */
+/* Sparse form of the fold matrices (mdctransformer.py:192-229 F, :176-190 inv(F)); h = N/2 pairs.
+ *   fold[4p..4p+3]   = { F[p, h-1-p], F[N-1-p, h-1-p], F[p, h+p], F[N-1-p, h+p] }
+ *   unfold[4p..4p+3] = { Finv[h-1-p, p], Finv[h+p, p], Finv[h-1-p, N-1-p], Finv[h+p, N-1-p] }
+ * precompute_f32 != 0 evaluates the window in float32 (precompute_dtype=tf.float32). */
+int ac_mdct_tables_host(int filters_n, int window_type, int precompute_f32, double* fold, double* unfold);
+
+/* Dense tables of PsychoacousticModel.__init__ (psychoacoustic.py:61-69), float64 precompute, cast to fp32:
+ *   W [N, nb], W_inv [nb, N], quiet [nb], spreading [nb, nb];
+ *   scalars[0..3] = { max_frequency, max_bark, bark_band_width, dB_MIN }.  Any output may be NULL. */
+int ac_pa_tables_host(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha,
+                      float* W, float* W_inv, float* quiet, float* spreading, double* scalars);
+
+/* ------------------------------------------------------------------------------------------- MDCT */
+/* MDCTransformer.__init__ (mdctransformer.py:13-59).  filters_n must be even (AC_ERR_INVALID otherwise,
+ * the reference asserts at :26).  Tables go to the current device. */
+int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_mdct_plan** out);
+int ac_mdct_plan_destroy(ac_mdct_plan* plan);
+
+/* MDCTransformer.transform (mdctransformer.py:61-125):  x [B, S, C] -> y [B, S/N + 1, N, C].
+ * S must be a multiple of filters_n (the reference raises at :287). */
+int ac_mdct_forward_f32(const ac_mdct_plan* plan, const float* x, float* y,
+                        int64_t batches, int64_t samples, int channels, void* stream);
+
+/* MDCTransformer.inverse_transform (mdctransformer.py:127-153):  y [B, M, N, C] -> x [B, (M+1) N, C]. */
+int ac_mdct_inverse_f32(const ac_mdct_plan* plan, const float* y, float* x,
+                        int64_t batches, int64_t blocks, int channels, void* stream);
+
+/* Decoder fusion: inverse_transform(q * thr) without materialising the dequantised amplitudes.
+ * q int32 [B, M, N, C], thr fp32 [B, M, N, C]. */
+int ac_mdct_inverse_dequant_f32(const ac_mdct_plan* plan, const int32_t* q, const float* thr, float* x,
+                                int64_t batches, int64_t blocks, int channels, void* stream);
+
+/* ---------------------------------------------------------------------------------- psychoacoustics */
+/* PsychoacousticModel.__init__ (psychoacoustic.py:14-69); compute dtype fp32, precompute float64. */
+int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha, ac_pa_plan** out);
+int ac_pa_plan_destroy(ac_pa_plan* plan);
+
+/* PsychoacousticModel.tonality (psychoacoustic.py:102-120):  y [B, M, N, C] -> ton [B, M, 1, C]. */
+int ac_pa_tonality_f32(const ac_pa_plan* plan, const float* y, float* ton,
+                       int64_t batches, int64_t blocks, int channels, void* stream);
+
+/* PsychoacousticModel.global_masking_threshold (psychoacoustic.py:122-148, 169-210, 301-331):
+ * y [B, M, N, C], ton [B, M, 1, C] (NULL = compute the tonality of y internally) -> thr [B, M, N, C]. */
+int ac_pa_threshold_f32(const ac_pa_plan* plan, const float* y, const float* ton, float drown, float* thr,
+                        int64_t batches, int64_t blocks, int channels, void* stream);
+
+/* Encoder fusion: tonality -> threshold -> q = rint(y / (thr_scale * thr)) in one pass over y.
+ * thr_out (may be NULL) receives thr_scale * thr, i.e. the step actually used; q int32 [B, M, N, C]. */
+int ac_pa_encode_f32(const ac_pa_plan* plan, const float* y, float drown, float thr_scale,
+                     float* thr_out, int32_t* q,
+                     int64_t batches, int64_t blocks, int channels, void* stream);
+
+/* PsychoacousticModel.add_noise (psychoacoustic.py:150-167): out = y + thr * N(0, 1/6), counter-based RNG. */
+int ac_pa_add_noise_f32(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, void* stream);
+
+/* -------------------------------------------------------------------------------------- quantiser */
+/* Build-defined (the reference has no quantiser; spec from add_noise, psychoacoustic.py:150-167):
+ * q = rint(y / thr) with IEEE division and round-half-even;  y_hat = q * thr. */
+int ac_quantize_f32(const float* y, const float* thr, int32_t* q, int64_t n, void* stream);
+int ac_dequantize_f32(const int32_t* q, const float* thr, float* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------ DLPack */
+/* Same operations on DLManagedTensor* (what `tensor.__dlpack__()` / tf.experimental.dlpack.to_dlpack put
+ * in the "dltensor" capsule).  Tensors are validated (kDLCUDA, float32 / int32, rank, compact strides,
+ * 16-byte alignment incl. byte_offset) and never copied or consumed: the caller keeps ownership. */
+int ac_mdct_forward_dl(const ac_mdct_plan* plan, struct DLManagedTensor* x, struct DLManagedTensor* y, void* stream);
+int ac_mdct_inverse_dl(const ac_mdct_plan* plan, struct DLManagedTensor* y, struct DLManagedTensor* x, void* stream);
+int ac_pa_tonality_dl(const ac_pa_plan* plan, struct DLManagedTensor* y, struct DLManagedTensor* ton, void* stream);
+int ac_pa_threshold_dl(const ac_pa_plan* plan, struct DLManagedTensor* y, struct DLManagedTensor* ton_or_null,
+                       float drown, struct DLManagedTensor* thr, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIOCODEC_B200_H_ */

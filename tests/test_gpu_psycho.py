@@ -1,0 +1,193 @@
+"""GPU parity tests of the psychoacoustic kernels and the quantiser against the oracle and reference fixtures.
+
+Tolerances (BASELINE.json north_star): masking threshold within 1e-5 relative to signal RMS; quantised
+integers bit-exact given the reference's threshold; end to end >= 99.99 % identical, remainder +-1.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import audiocodec_b200
+from audiocodec_b200 import _capi
+from oracle import audiocodec_oracle as oracle
+from conftest import rms
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a):
+  return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def sine_wav(amplitude, frequency, sample_rate, duration_sec):
+  t = np.arange(0, sample_rate * duration_sec, dtype=np.float32)
+  return (amplitude * np.sin(2.0 * np.pi * frequency * t / sample_rate)).astype(np.float32).reshape(1, -1, 1)
+
+
+# ---- the reference's own tests, on the CUDA path -----------------------------------------------------------
+def test_tonality_tone():
+  """audiocodec/tests/test_psychoacoustic.py:32-42."""
+  y = audiocodec_b200.MDCTransformer(64).transform(cuda(sine_wav(0.8, 4, 64, 5.)))
+  ton = audiocodec_b200.PsychoacousticModel(sample_rate=64, filter_bands_n=64).tonality(y)
+  assert ton[0, 1].item() == 1.0
+
+
+def test_tonality_noise():
+  """audiocodec/tests/test_psychoacoustic.py:44-65."""
+  x = torch.rand(10, 640, 2, device="cuda") * 2 - 1
+  y = audiocodec_b200.MDCTransformer(64).transform(x)
+  ton = audiocodec_b200.PsychoacousticModel(sample_rate=64, filter_bands_n=64).tonality(y)
+  assert tuple(ton.shape) == (10, 11, 1, 2)
+  assert ton[0, 1:-1].mean().item() < 0.1
+
+
+# ---- reference fixtures ------------------------------------------------------------------------------------
+PA_CASES = [("n256", 44100, 256, 64, 0.6), ("n1024", 48000, 1024, 64, 0.6), ("n64", 32768, 64, 64, 0.6),
+            ("n128_nb24", 16000, 128, 24, 0.8)]
+
+
+@pytest.mark.parametrize("name,sr,n,nb,alpha", PA_CASES)
+def test_against_reference_fixture(golden, name, sr, n, nb, alpha):
+  pa = audiocodec_b200.PsychoacousticModel(sr, n, nb, alpha)
+  y = golden[f"pa_{name}_f32_y"]
+  y64 = golden[f"pa_{name}_f64_y"]
+  assert np.max(np.abs(y - y64)) < 1e-6          # same amplitudes up to fp32 rounding
+  signal_rms = rms(golden[f"pa_{name}_x"])
+  ton = pa.tonality(cuda(y)).cpu().numpy()
+  ton_ref = golden[f"pa_{name}_f64_ton"]
+  assert ton.shape == ton_ref.shape
+  assert np.max(np.abs(ton - ton_ref)) < 2e-5
+  for key, drown in (("thr", 0.0), ("thr_drown", 0.35)):
+    thr_ref = golden[f"pa_{name}_f64_{key}"]
+    thr = pa.global_masking_threshold(cuda(y), cuda(golden[f"pa_{name}_f32_ton"]), drown=drown).cpu().numpy()
+    assert thr.shape == thr_ref.shape
+    assert np.max(np.abs(thr - thr_ref)) <= 1e-5 * signal_rms        # the north-star tolerance
+    np.testing.assert_allclose(thr, thr_ref, rtol=2e-4)              # and tight relative to thr itself
+    assert thr.min() >= 1e-7 * (1 - 1e-6)
+    fused = pa.global_masking_threshold(cuda(y), None, drown=drown).cpu().numpy()   # internal tonality
+    np.testing.assert_allclose(fused, thr_ref, rtol=2e-4)
+
+
+@pytest.mark.parametrize("sr,n,nb,alpha,b,m,c", [(44100, 256, 64, 0.6, 3, 17, 2), (48000, 1024, 64, 0.6, 2, 9, 2),
+                                                   (22050, 512, 48, 0.5, 2, 5, 1), (44100, 2048, 64, 0.6, 1, 3, 2),
+                                                   (8000, 32, 16, 1.0, 2, 6, 3), (44100, 100, 40, 0.6, 2, 4, 1)])
+def test_against_oracle_random_spectra(sr, n, nb, alpha, b, m, c):
+  rng = np.random.default_rng(n + nb)
+  # spectra with a large dynamic range, including exact zeros
+  y = (rng.standard_normal((b, m, n, c)) * 10.0 ** rng.uniform(-6, 0, (b, m, n, c))).astype(np.float32)
+  y[0, 0] = 0.0
+  y[-1, -1, ::3] = 0.0
+  ref = oracle.PsychoacousticModel(sr, n, nb, alpha, compute_dtype=np.float64)
+  pa = audiocodec_b200.PsychoacousticModel(sr, n, nb, alpha)
+  ton = pa.tonality(cuda(y))
+  ton_ref = ref.tonality(y.astype(np.float64))
+  assert np.max(np.abs(ton.cpu().numpy() - ton_ref)) < 2e-5
+  for drown in (0.0, 1.0):
+    thr = pa.global_masking_threshold(cuda(y), ton, drown=drown).cpu().numpy()
+    thr_ref = ref.global_masking_threshold(y.astype(np.float64), ton_ref, drown=drown)
+    np.testing.assert_allclose(thr, thr_ref, rtol=3e-4)
+    assert np.max(np.abs(thr - thr_ref)) <= 1e-5 * max(rms(y), 1e-3)
+
+
+# ---- quantiser ----------------------------------------------------------------------------------------------
+def test_quantizer_bit_exact_given_reference_threshold(golden):
+  for name, sr, n, nb, alpha in PA_CASES:
+    y = golden[f"pa_{name}_f32_y"]
+    thr = golden[f"pa_{name}_f32_thr"]
+    pa = audiocodec_b200.PsychoacousticModel(sr, n, nb, alpha)
+    q = pa.quantize(cuda(y), cuda(thr))
+    q_ref = oracle.quantize(y, thr)
+    assert q.dtype == torch.int32
+    assert np.array_equal(q.cpu().numpy(), q_ref)
+    deq = pa.dequantize(q, cuda(thr)).cpu().numpy()
+    assert np.array_equal(deq, oracle.dequantize(q_ref, thr))
+
+
+def test_quantizer_half_way_cases():
+  a = torch.tensor([0.5, 1.5, 2.5, -0.5, -1.5, 0.26, -3.49, 7.5], device="cuda")
+  pa = audiocodec_b200.PsychoacousticModel(44100, 8)
+  q = pa.quantize(a.reshape(1, 1, 8, 1), torch.ones(1, 1, 8, 1, device="cuda"))
+  assert q.flatten().tolist() == [0, 2, 2, 0, -2, 0, -3, 8]
+
+
+@pytest.mark.parametrize("sr,n,c", [(44100, 256, 2), (48000, 1024, 2), (44100, 256, 1)])
+def test_end_to_end_quantised_integers(sr, n, c):
+  """x -> q on the GPU vs the fp32-faithful oracle: >= 99.99 % identical, the rest +-1."""
+  b, blocks = 4, 40
+  x = oracle.synthetic_audio(b, blocks * n, c, sr)
+  codec = audiocodec_b200.AudioCodec(sr, filters_n=n)
+  q, step = codec.encode(cuda(x))
+  mdct = oracle.MDCTransformer(n, compute_dtype=np.float32)
+  pa = oracle.PsychoacousticModel(sr, n, compute_dtype=np.float32)
+  y_ref = mdct.transform(x)
+  thr_ref = pa.global_masking_threshold(y_ref, pa.tonality(y_ref))
+  q_ref = oracle.quantize(y_ref, thr_ref)
+  diff = np.abs(q.cpu().numpy().astype(np.int64) - q_ref)
+  assert diff.max() <= 1
+  assert np.mean(diff == 0) >= 0.9999, np.mean(diff == 0)
+  assert np.max(np.abs(step.cpu().numpy() - thr_ref)) <= 1e-5 * rms(x)
+  # and the decoder: same reconstruction error as the reference chain, inside the north-star tolerance
+  xhat = codec.decode(q, step).cpu().numpy()[:, n:-n]
+  xhat_ref = mdct.inverse_transform(oracle.dequantize(q_ref, thr_ref))[:, n:-n]
+  err, err_ref = rms(xhat - x), rms(xhat_ref - x)
+  assert abs(err - err_ref) <= 1e-3 * err_ref
+
+
+def test_encode_matches_unfused_chain():
+  x = cuda(oracle.synthetic_audio(3, 256 * 30, 2, 44100))
+  codec = audiocodec_b200.AudioCodec(44100, filters_n=256)
+  y = codec.mdct.transform(x)
+  pa = codec.psychoacoustic
+  thr = pa.global_masking_threshold(y, pa.tonality(y))
+  q, step = pa.encode(y)
+  np.testing.assert_allclose(step.cpu().numpy(), thr.cpu().numpy(), rtol=1e-5)
+  assert torch.equal(q, pa.quantize(y, step))
+  q2, step2 = pa.encode(y, thr_scale=2.0)
+  np.testing.assert_allclose(step2.cpu().numpy(), 2 * step.cpu().numpy(), rtol=1e-6)
+  assert torch.equal(pa.encode(y, return_threshold=False), q)
+
+
+def test_full_size_threshold_properties_cfg4_slice():
+  """Size-independent properties on a large batch: thr >= 1e-7, scale covariance, drown monotonicity."""
+  sr, n = 44100, 256
+  x = torch.rand(64, n * 431, 1, device="cuda") - 0.5
+  y = audiocodec_b200.MDCTransformer(n).transform(x)
+  pa = audiocodec_b200.PsychoacousticModel(sr, n)
+  thr = pa.global_masking_threshold(y, None)
+  assert thr.min().item() >= 1e-7 * (1 - 1e-6) and torch.isfinite(thr).all()
+  louder = pa.global_masking_threshold(2 * y, None)
+  assert (louder >= thr * (1 - 1e-5)).all()           # more signal never lowers the threshold
+  drowned = pa.global_masking_threshold(y, None, drown=1.0)
+  assert (drowned >= thr * (1 - 1e-5)).all()          # drown=1 -> offset 0 -> maximal masking (:185)
+  ton = pa.tonality(y)
+  assert ton.max().item() <= 1.0
+
+
+def test_add_noise_statistics():
+  pa = audiocodec_b200.PsychoacousticModel(44100, 256)
+  a = torch.zeros(8, 64, 256, 2, device="cuda")
+  thr = torch.full_like(a, 0.6)
+  noisy = pa.add_noise(a, thr, seed=42)
+  assert abs(noisy.mean().item()) < 1e-3
+  assert abs(noisy.std().item() - 0.1) < 1e-3          # sigma = thr / 6  (psychoacoustic.py:154-156)
+  assert torch.equal(noisy, pa.add_noise(a, thr, seed=42))
+  assert not torch.equal(noisy, pa.add_noise(a, thr, seed=43))
+  z = (noisy / 0.1).flatten()
+  assert abs((z ** 4).mean().item() - 3.0) < 0.05      # gaussian kurtosis
+
+
+def test_dlpack_entry_points(golden):
+  y = cuda(golden["pa_n256_f32_y"])
+  pa = audiocodec_b200.PsychoacousticModel(44100, 256)
+  ton_ptr = pa.tonality(y)
+  thr_ptr = pa.global_masking_threshold(y, ton_ptr, drown=0.1)
+  ton, thr = torch.empty_like(ton_ptr), torch.empty_like(thr_ptr)
+  cy, ct, ch = y.__dlpack__(), ton.__dlpack__(), thr.__dlpack__()
+  stream = torch.cuda.current_stream().cuda_stream
+  plan = pa._plan(y.device)
+  _capi.check(_capi.lib().ac_pa_tonality_dl(plan, _capi.dl_pointer(cy), _capi.dl_pointer(ct), stream))
+  _capi.check(_capi.lib().ac_pa_threshold_dl(plan, _capi.dl_pointer(cy), _capi.dl_pointer(ct), 0.1, _capi.dl_pointer(ch), stream))
+  assert torch.equal(ton, ton_ptr) and torch.equal(thr, thr_ptr)
+  _capi.check(_capi.lib().ac_pa_threshold_dl(plan, _capi.dl_pointer(cy), None, 0.1, _capi.dl_pointer(ch), stream))
+  np.testing.assert_allclose(thr.cpu().numpy(), thr_ptr.cpu().numpy(), rtol=1e-5)

@@ -1,0 +1,120 @@
+"""CPU-only checks of the host side: the C library loads, exports the whole header, and its float64 table
+builders agree with the oracle (and through it with the reference's golden fixtures).  No kernel runs here."""
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import audiocodec_b200
+from audiocodec_b200 import _capi
+from oracle import audiocodec_oracle as oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+  header = open(os.path.join(ROOT, "include", "audiocodec_b200.h")).read()
+  header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+  declared = set(re.findall(r"\b(ac_[a-z0-9_]+)\s*\(", header))
+  assert len(declared) >= 20
+  handle = ctypes.CDLL(_capi.library_path())
+  for name in sorted(declared):
+    assert hasattr(handle, name), f"{name} declared in the header but not exported"
+  assert declared == set(_capi.SIGNATURES), "ctypes signature table out of sync with the header"
+  assert _capi.lib().ac_abi_version() == 1
+
+
+@pytest.mark.parametrize("n,window", [(8, 'vorbis'), (16, 'sine'), (12, 'ones'), (64, 'vorbis'), (256, 'vorbis'),
+                                      (1024, 'sine')])
+def test_mdct_tables_match_oracle(n, window):
+  ours = audiocodec_b200.MDCTransformer(n, window_type=window)
+  ref = oracle.MDCTransformer(n, window_type=window, compute_dtype=np.float32)
+  assert ours.H.shape == (2, n, n) and ours.H.dtype == torch.float32
+  assert np.max(np.abs(ours.H.numpy() - ref.H)) <= 1e-7
+  assert np.max(np.abs(ours.H_inv.numpy() - ref.H_inv)) <= 2e-7
+  assert np.count_nonzero(ours.H.numpy()) <= 2 * n
+
+
+def test_mdct_tables_match_reference_fixture(golden):
+  for n, window in [(8, 'vorbis'), (16, 'sine'), (12, 'ones'), (64, 'vorbis')]:
+    ours = audiocodec_b200.MDCTransformer(n, window_type=window)
+    assert np.max(np.abs(ours.H.numpy() - golden[f"H_{n}_{window}"])) <= 6e-8
+    assert np.max(np.abs(ours.H_inv.numpy() - golden[f"Hinv_{n}_{window}"])) <= 6e-8
+
+
+def test_mdct_float32_precompute_variant():
+  a = audiocodec_b200.MDCTransformer(64, precompute_dtype='float32')
+  b = oracle.MDCTransformer(64, precompute_dtype=np.float32)
+  # float32 sin() implementations differ by an ulp and the consistency rule (mdctransformer.py:219-221)
+  # amplifies that by 1 / w[0]; agreement is to a few float32 ulps, not bit-exact
+  assert np.max(np.abs(a.H.numpy() - b.H)) <= 5e-6
+
+
+@pytest.mark.parametrize("sr,n,nb,alpha", [(32768, 64, 64, 0.6), (44100, 256, 64, 0.6), (48000, 1024, 64, 0.6),
+                                           (16000, 128, 24, 0.8)])
+def test_pa_tables_match_oracle_and_fixture(golden, sr, n, nb, alpha):
+  ours = audiocodec_b200.PsychoacousticModel(sr, n, nb, alpha)
+  ref = oracle.PsychoacousticModel(sr, n, nb, alpha, compute_dtype=np.float32)
+  assert np.array_equal(ours.W.numpy(), ref.W)
+  assert np.array_equal(ours.W_inv.numpy(), ref.W_inv)
+  np.testing.assert_allclose(ours.quiet_threshold_intensity.numpy(), ref.quiet_threshold_intensity, rtol=2e-7)
+  np.testing.assert_allclose(ours.spreading_matrix.numpy(), ref.spreading_matrix, rtol=2e-7)
+  key = f"pa_{sr}_{n}_{nb}"
+  np.testing.assert_allclose(ours.spreading_matrix.numpy(), golden[f"{key}_S"], rtol=2e-7)
+  np.testing.assert_allclose(ours.W.numpy(), golden[f"{key}_W"], atol=6e-8)
+  assert abs(ours.max_bark - golden[f"{key}_scalars"][0]) < 1e-12
+  assert abs(ours._dB_MIN - golden[f"{key}_scalars"][2]) < 1e-5
+  # reference unit tests test_psychoacoustic.py:14-30
+  assert float(torch.sum(torch.abs(ours.W.sum(dim=1) - 1.0))) < 1e-5
+  assert float(torch.sum(torch.abs(ours.W_inv.sum(dim=1) - 1.0))) < 1e-5
+
+
+def test_constructor_errors_match_reference():
+  with pytest.raises(AssertionError):
+    audiocodec_b200.MDCTransformer(7)                          # mdctransformer.py:26
+  with pytest.raises(AttributeError):
+    audiocodec_b200.MDCTransformer(8, window_type=None)        # mdctransformer.py:199 (.lower() on None)
+  with pytest.raises(TypeError):
+    audiocodec_b200.PsychoacousticModel(44100, compute_dtype='float16')   # psychoacoustic.py:42-43
+  with pytest.raises(NotImplementedError):
+    audiocodec_b200.PsychoacousticModel(44100, compute_dtype='bfloat16')
+  with pytest.raises(TypeError):
+    audiocodec_b200.MDCTransformer(8, compute_dtype='int32')
+  assert audiocodec_b200.MDCTransformer(8, compute_dtype=torch.float32).compute_dtype == "float32"
+  assert audiocodec_b200.MDCTransformer(8, compute_dtype=np.float32).compute_dtype == "float32"
+
+
+def test_no_cpu_path():
+  """Host tensors are refused: the product has no CPU fallback."""
+  m = audiocodec_b200.MDCTransformer(8)
+  with pytest.raises(RuntimeError, match="no CPU path"):
+    m.transform(torch.zeros(1, 16, 1))
+  with pytest.raises(TypeError):
+    m.transform(torch.zeros(1, 16, 1, dtype=torch.float64))
+  pa = audiocodec_b200.PsychoacousticModel(32768, 8)
+  with pytest.raises(RuntimeError, match="no CPU path"):
+    pa.tonality(torch.zeros(1, 2, 8, 1))
+
+
+def test_utilities():
+  pa = audiocodec_b200.PsychoacousticModel(44100, 64)
+  ref = oracle.PsychoacousticModel(44100, 64)
+  a = np.asarray([0., 1e-9, 1e-3, 0.5, 1.0], np.float32)
+  np.testing.assert_allclose(pa.amplitude_to_dB(torch.from_numpy(a)).numpy(), ref.amplitude_to_dB(a), rtol=1e-6)
+  np.testing.assert_allclose(pa.amplitude_to_dB_norm(torch.from_numpy(a)).numpy(), ref.amplitude_to_dB_norm(a),
+                             rtol=1e-5, atol=1e-6)
+  assert abs(float(pa.bark2freq(pa.freq2bark(1234.5))) - 1234.5) < 1e-9
+
+
+def test_product_does_not_import_oracle():
+  """The oracle is test infrastructure; nothing under audiocodec_b200/ may reference it."""
+  pkg = os.path.join(ROOT, "audiocodec_b200")
+  for dirpath, _, files in os.walk(pkg):
+    for name in files:
+      if name.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+        text = open(os.path.join(dirpath, name)).read()
+        assert "oracle" not in text.replace("the oracle", "").replace("The oracle", ""), name
