@@ -26,4 +26,6 @@ def golden():
 
 def rms(a):
   a = np.asarray(a, dtype=np.float64)
+  if a.size == 0:
+    return 0.0
   return float(np.sqrt(np.mean(a * a)))
