@@ -4,6 +4,7 @@
 #include "kernels.h"
 #include "tables.h"
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdarg>
@@ -308,6 +309,47 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
   d.eps = 1e-14f;
   d.max_band_cnt = t.max_band_cnt;
   d.max_filt_cnt = t.max_filt_cnt;
+  d.band_nnz = static_cast<int>(t.band_w.size());
+  d.filt_nnz = static_cast<int>(t.filt_w.size());
+  d.gain_log2 = static_cast<float>(-alpha * std::log2(10.0) / 10.0);
+  std::vector<int32_t> filt_pack(t.n, 0);
+  const bool packable = t.nb <= 255 && t.max_filt_cnt <= 255 && t.filt_w.size() < 65536;
+  if (packable)
+    for (int k = 0; k < t.n; ++k) filt_pack[k] = t.filt_b0[k] | (t.filt_cnt[k] << 8) | (t.filt_ptr[k] << 16);
+  // tile kernel tables: chunks of 256 filters, bands of each chunk split four ways by cost
+  d.chunk_k = 256;
+  d.n_chunks = (t.n + d.chunk_k - 1) / d.chunk_k;
+  d.tile_ok = (packable && t.nb == 64 && t.max_filt_cnt <= 3) ? 1 : 0;
+  std::vector<int32_t> chunk_split(static_cast<size_t>(d.n_chunks) * 5, 0);
+  for (int c = 0; c < d.n_chunks; ++c) {
+    const int kc0 = c * d.chunk_k, kc1 = std::min(t.n, kc0 + d.chunk_k);
+    int first = t.nb, last = -1;
+    std::vector<double> cost(t.nb, 0.0);
+    for (int i = 0; i < t.nb; ++i) {
+      const int ka = std::max(t.band_k0[i], kc0), kb = std::min(t.band_k0[i] + t.band_cnt[i], kc1);
+      if (kb > ka) {
+        first = std::min(first, i);
+        last = std::max(last, i);
+        cost[i] = (kb - ka) + 8.0;   // filters summed + a fixed cost per band (the power at the band's end)
+      }
+    }
+    int32_t* sp = &chunk_split[static_cast<size_t>(c) * 5];
+    if (last < first) {
+      for (int w = 0; w <= 4; ++w) sp[w] = 0;
+      continue;
+    }
+    double total = 0;
+    for (int i = first; i <= last; ++i) total += cost[i];
+    double run = 0;
+    int w = 1;
+    sp[0] = first;
+    for (int i = first; i <= last && w < 4; ++i) {
+      run += cost[i];
+      if (run >= total * w / 4.0) sp[w++] = i + 1;
+    }
+    for (; w <= 4; ++w) sp[w] = last + 1;
+    sp[4] = last + 1;
+  }
   std::vector<float> quiet(t.quiet.begin(), t.quiet.end()), spread(t.spread_fn.begin(), t.spread_fn.end());
   if ((err = upload(t.band_k0, &d.band_k0, plan->owned)) != cudaSuccess ||
       (err = upload(t.band_cnt, &d.band_cnt, plan->owned)) != cudaSuccess ||
@@ -319,7 +361,9 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
       (err = upload(t.filt_w, &d.filt_w, plan->owned)) != cudaSuccess ||
       (err = upload(quiet, &d.quiet, plan->owned)) != cudaSuccess ||
       (err = upload(spread, &d.spread_fn, plan->owned)) != cudaSuccess ||
-      (err = upload(t.lin, &d.lin, plan->owned)) != cudaSuccess) {
+      (err = upload(t.lin, &d.lin, plan->owned)) != cudaSuccess ||
+      (err = upload(filt_pack, &d.filt_pack, plan->owned)) != cudaSuccess ||
+      (err = upload(chunk_split, &d.chunk_split, plan->owned)) != cudaSuccess) {
     free_all(plan->owned);
     delete plan;
     return cuda_fail(err, "uploading psychoacoustic tables");

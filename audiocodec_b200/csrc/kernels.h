@@ -40,6 +40,14 @@ struct PaDeviceTables {
   const float* quiet = nullptr;       // [nb]
   const float* spread_fn = nullptr;   // [2 nb]
   const float* lin = nullptr;         // [nb]
+  // tile kernel (nb == 64): the filter axis is processed in chunks of chunk_k filters; in chunk c the bands
+  // [chunk_split[5c + w], chunk_split[5c + w + 1]) are summed by warp w of a 4-warp CTA (balanced by work).
+  // filt_pack[k] = first band | count << 8 | offset into filt_w << 16.
+  int chunk_k = 0, n_chunks = 0, tile_ok = 0;
+  int band_nnz = 0, filt_nnz = 0;
+  const int32_t* chunk_split = nullptr;
+  const int32_t* filt_pack = nullptr;
+  float gain_log2 = 0.f;    // fp32(-alpha * log2(10) / 10): gain = 2^(gain_log2 * offset)   (psychoacoustic.py:197)
 };
 
 void count_launch();
