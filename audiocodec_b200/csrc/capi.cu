@@ -309,46 +309,61 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
   d.eps = 1e-14f;
   d.max_band_cnt = t.max_band_cnt;
   d.max_filt_cnt = t.max_filt_cnt;
-  d.band_nnz = static_cast<int>(t.band_w.size());
-  d.filt_nnz = static_cast<int>(t.filt_w.size());
   d.gain_log2 = static_cast<float>(-alpha * std::log2(10.0) / 10.0);
-  std::vector<int32_t> filt_pack(t.n, 0);
-  const bool packable = t.nb <= 255 && t.max_filt_cnt <= 255 && t.filt_w.size() < 65536;
-  if (packable)
-    for (int k = 0; k < t.n; ++k) filt_pack[k] = t.filt_b0[k] | (t.filt_cnt[k] << 8) | (t.filt_ptr[k] << 16);
-  // tile kernel tables: chunks of 256 filters, bands of each chunk split four ways by cost
+  // ---- tile-kernel tables: chunks of 256 filters; in every chunk the bands are split four ways by cost
   d.chunk_k = 256;
   d.n_chunks = (t.n + d.chunk_k - 1) / d.chunk_k;
-  d.tile_ok = (packable && t.nb == 64 && t.max_filt_cnt <= 3) ? 1 : 0;
-  std::vector<int32_t> chunk_split(static_cast<size_t>(d.n_chunks) * 5, 0);
+  d.tile_ok = (t.nb == 64 && t.max_filt_cnt <= 3) ? 1 : 0;
+  std::vector<int4> band_desc;
+  std::vector<float> band_w4;
+  std::vector<int32_t> desc_start(static_cast<size_t>(d.n_chunks) * 5 + 1, 0);
   for (int c = 0; c < d.n_chunks; ++c) {
     const int kc0 = c * d.chunk_k, kc1 = std::min(t.n, kc0 + d.chunk_k);
-    int first = t.nb, last = -1;
-    std::vector<double> cost(t.nb, 0.0);
+    std::vector<int> bands;
+    std::vector<double> cost;
+    double total = 0;
     for (int i = 0; i < t.nb; ++i) {
       const int ka = std::max(t.band_k0[i], kc0), kb = std::min(t.band_k0[i] + t.band_cnt[i], kc1);
       if (kb > ka) {
-        first = std::min(first, i);
-        last = std::max(last, i);
-        cost[i] = (kb - ka) + 8.0;   // filters summed + a fixed cost per band (the power at the band's end)
+        bands.push_back(i);
+        const bool final = t.band_k0[i] + t.band_cnt[i] <= kc1;
+        cost.push_back(12.0 + 12.0 * ((kb - ka + 3) / 4) + (final ? 24.0 : 0.0));   // ~instructions per lane
+        total += cost.back();
       }
     }
-    int32_t* sp = &chunk_split[static_cast<size_t>(c) * 5];
-    if (last < first) {
-      for (int w = 0; w <= 4; ++w) sp[w] = 0;
-      continue;
-    }
-    double total = 0;
-    for (int i = first; i <= last; ++i) total += cost[i];
     double run = 0;
-    int w = 1;
-    sp[0] = first;
-    for (int i = first; i <= last && w < 4; ++i) {
-      run += cost[i];
-      if (run >= total * w / 4.0) sp[w++] = i + 1;
+    int w = 0;
+    desc_start[static_cast<size_t>(c) * 5] = static_cast<int32_t>(band_desc.size());
+    for (size_t b = 0; b < bands.size(); ++b) {
+      const int i = bands[b];
+      const int ka = std::max(t.band_k0[i], kc0), kb = std::min(t.band_k0[i] + t.band_cnt[i], kc1);
+      const int steps = (kb - ka + 3) / 4;
+      int4 ds;
+      ds.x = ka - kc0;
+      ds.y = steps;
+      ds.z = static_cast<int>(band_w4.size());
+      ds.w = i | (t.band_k0[i] < kc0 ? 0x100 : 0) | (t.band_k0[i] + t.band_cnt[i] <= kc1 ? 0x200 : 0);
+      for (int s = 0; s < 4 * steps; ++s)
+        band_w4.push_back(ka + s < kb ? t.band_w[t.band_ptr[i] + (ka + s - t.band_k0[i])] : 0.f);
+      band_desc.push_back(ds);
+      run += cost[b];
+      while (w < 3 && run >= total * (w + 1) / 4.0) desc_start[static_cast<size_t>(c) * 5 + (++w)] = static_cast<int32_t>(band_desc.size());
     }
-    for (; w <= 4; ++w) sp[w] = last + 1;
-    sp[4] = last + 1;
+    while (w < 4) desc_start[static_cast<size_t>(c) * 5 + (++w)] = static_cast<int32_t>(band_desc.size());
+  }
+  desc_start[static_cast<size_t>(d.n_chunks) * 5] = static_cast<int32_t>(band_desc.size());
+  d.n_desc = static_cast<int>(band_desc.size());
+  d.n_band_w4 = static_cast<int>(band_w4.size());
+  std::vector<float4> filt4(t.n, make_float4(0.f, 0.f, 0.f, 0.f));
+  if (d.tile_ok) {
+    for (int k = 0; k < t.n; ++k) {
+      const int b0 = std::max(0, std::min(t.filt_b0[k], t.nb - 3));
+      float w3[3] = {0.f, 0.f, 0.f};
+      for (int s = 0; s < t.filt_cnt[k]; ++s) w3[t.filt_b0[k] + s - b0] = t.filt_w[t.filt_ptr[k] + s];
+      float b0f;
+      std::memcpy(&b0f, &b0, sizeof(float));
+      filt4[k] = make_float4(w3[0], w3[1], w3[2], b0f);
+    }
   }
   std::vector<float> quiet(t.quiet.begin(), t.quiet.end()), spread(t.spread_fn.begin(), t.spread_fn.end());
   if ((err = upload(t.band_k0, &d.band_k0, plan->owned)) != cudaSuccess ||
@@ -362,8 +377,10 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
       (err = upload(quiet, &d.quiet, plan->owned)) != cudaSuccess ||
       (err = upload(spread, &d.spread_fn, plan->owned)) != cudaSuccess ||
       (err = upload(t.lin, &d.lin, plan->owned)) != cudaSuccess ||
-      (err = upload(filt_pack, &d.filt_pack, plan->owned)) != cudaSuccess ||
-      (err = upload(chunk_split, &d.chunk_split, plan->owned)) != cudaSuccess) {
+      (err = upload(band_desc, &d.band_desc, plan->owned)) != cudaSuccess ||
+      (err = upload(band_w4, &d.band_w4, plan->owned)) != cudaSuccess ||
+      (err = upload(desc_start, &d.desc_start, plan->owned)) != cudaSuccess ||
+      (err = upload(filt4, &d.filt4, plan->owned)) != cudaSuccess) {
     free_all(plan->owned);
     delete plan;
     return cuda_fail(err, "uploading psychoacoustic tables");

@@ -40,13 +40,17 @@ struct PaDeviceTables {
   const float* quiet = nullptr;       // [nb]
   const float* spread_fn = nullptr;   // [2 nb]
   const float* lin = nullptr;         // [nb]
-  // tile kernel (nb == 64): the filter axis is processed in chunks of chunk_k filters; in chunk c the bands
-  // [chunk_split[5c + w], chunk_split[5c + w + 1]) are summed by warp w of a 4-warp CTA (balanced by work).
-  // filt_pack[k] = first band | count << 8 | offset into filt_w << 16.
+  // tile kernel (nb == 64, <= 3 bands per filter): the filter axis is processed in chunks of chunk_k filters.
+  //   band_desc[d] = { row of the band's first filter inside the chunk, number of 4-filter steps,
+  //                    offset into band_w4 (zero-padded to whole steps), band | add-partial << 8 | final << 9 }
+  //   desc_start[5 c + w] .. desc_start[5 c + w + 1]: the descriptors warp w of a 4-warp CTA sums in chunk c
+  //   filt4[k] = { w0, w1, w2, first band (as int bits) }: W_inv weights of the three bands from `first band`
   int chunk_k = 0, n_chunks = 0, tile_ok = 0;
-  int band_nnz = 0, filt_nnz = 0;
-  const int32_t* chunk_split = nullptr;
-  const int32_t* filt_pack = nullptr;
+  int n_desc = 0, n_band_w4 = 0;
+  const int4* band_desc = nullptr;
+  const float* band_w4 = nullptr;
+  const int32_t* desc_start = nullptr;
+  const float4* filt4 = nullptr;
   float gain_log2 = 0.f;    // fp32(-alpha * log2(10) / 10): gain = 2^(gain_log2 * offset)   (psychoacoustic.py:197)
 };
 
