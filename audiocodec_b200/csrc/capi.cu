@@ -203,6 +203,41 @@ int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_m
     const double ra = -2.0 * pi * p / h;
     roots[p] = make_float2((float)std::cos(ra), (float)std::sin(ra));
   }
+  // tile-kernel tables (mdct_tile_kernels.cu); variant 0 reads / writes position p (or 2k) first, variant 1 the
+  // mirrored position N-1-p (or N-1-2k) first, so the coefficient pairs are swapped
+  std::vector<float4> pre_fwd(static_cast<size_t>(4) * h), post_fwd(static_cast<size_t>(2) * h);
+  std::vector<float4> pre_inv(static_cast<size_t>(2) * h), post_inv(static_cast<size_t>(2) * h);
+  for (int m = 0; m < h; ++m) {
+    const double ang = -pi * (m + 0.125) / n, c = std::cos(ang), s = std::sin(ang);
+    const bool low = m < h / 2;
+    const int p = low ? h - 1 - 2 * m : 2 * m - h;
+    double re[4], im[4];
+    if (p >= 0 && p < h) {
+      const double a0 = t.fold[4 * p], a1 = t.fold[4 * p + 1], a2 = t.fold[4 * p + 2], a3 = t.fold[4 * p + 3];
+      if (low) {   // z = alpha + i beta
+        re[0] = a0 * c; re[1] = a1 * c; re[2] = -a2 * s; re[3] = -a3 * s;
+        im[0] = a0 * s; im[1] = a1 * s; im[2] = a2 * c; im[3] = a3 * c;
+      } else {     // z = beta + i alpha
+        re[0] = -a0 * s; re[1] = -a1 * s; re[2] = a2 * c; re[3] = a3 * c;
+        im[0] = a0 * c; im[1] = a1 * c; im[2] = a2 * s; im[3] = a3 * s;
+      }
+    } else {
+      for (int i = 0; i < 4; ++i) re[i] = im[i] = 0.0;
+    }
+    pre_fwd[(0 * h + m) * 2] = make_float4((float)re[0], (float)re[1], (float)re[2], (float)re[3]);
+    pre_fwd[(0 * h + m) * 2 + 1] = make_float4((float)im[0], (float)im[1], (float)im[2], (float)im[3]);
+    pre_fwd[(1 * h + m) * 2] = make_float4((float)re[1], (float)re[0], (float)re[3], (float)re[2]);
+    pre_fwd[(1 * h + m) * 2 + 1] = make_float4((float)im[1], (float)im[0], (float)im[3], (float)im[2]);
+    // first store S1 = vx c0 + vy c1, second S2 = vx c2 + vy c3; variant 0: S1 = Re D -> [2k], S2 = -Im D -> [N-1-2k]
+    const double fx = c * scale_fwd, fy = s * scale_fwd, ix = c * scale_inv, iy = s * scale_inv;
+    post_fwd[0 * h + m] = make_float4((float)fx, (float)-fy, (float)-fy, (float)-fx);
+    post_fwd[1 * h + m] = make_float4((float)-fy, (float)-fx, (float)fx, (float)-fy);
+    post_inv[0 * h + m] = make_float4((float)ix, (float)-iy, (float)-iy, (float)-ix);
+    post_inv[1 * h + m] = make_float4((float)-iy, (float)-ix, (float)ix, (float)-iy);
+    // loads L1, L2 (variant 0: Y[2n], Y[N-1-2n]):  Re = L1 k0 + L2 k1,  Im = L1 k2 + L2 k3
+    pre_inv[0 * h + m] = make_float4((float)c, (float)-s, (float)s, (float)c);
+    pre_inv[1 * h + m] = make_float4((float)-s, (float)c, (float)c, (float)s);
+  }
   std::vector<float> cos_table;
   if (!fast) {
     cos_table.resize(static_cast<size_t>(8) * n);
@@ -217,7 +252,11 @@ int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_m
       (err = upload(twf, &plan->tb.tw_post_fwd, plan->owned)) != cudaSuccess ||
       (err = upload(twi, &plan->tb.tw_post_inv, plan->owned)) != cudaSuccess ||
       (err = upload(roots, &plan->tb.roots, plan->owned)) != cudaSuccess ||
-      (err = upload(cos_table, &plan->tb.cos_table, plan->owned)) != cudaSuccess) {
+      (err = upload(cos_table, &plan->tb.cos_table, plan->owned)) != cudaSuccess ||
+      (err = upload(pre_fwd, &plan->tb.pre_fwd, plan->owned)) != cudaSuccess ||
+      (err = upload(post_fwd, &plan->tb.post_fwd, plan->owned)) != cudaSuccess ||
+      (err = upload(pre_inv, &plan->tb.pre_inv, plan->owned)) != cudaSuccess ||
+      (err = upload(post_inv, &plan->tb.post_inv, plan->owned)) != cudaSuccess) {
     free_all(plan->owned);
     delete plan;
     return cuda_fail(err, "uploading MDCT tables");

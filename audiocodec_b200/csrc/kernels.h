@@ -19,6 +19,11 @@ struct MdctDeviceTables {
   const float2* tw_post_inv = nullptr;   // tw_pre * scale_inv
   const float2* roots = nullptr;     // [N/2]  exp(-2 pi i j / (N/2))
   const float* cos_table = nullptr;  // [8N]   cos(pi m / (4N)), generic-N path only
+  // tile kernels (mdct_tile_kernels.cu), [variant][n]: host-merged coefficients, see capi.cu
+  const float4* pre_fwd = nullptr;   // [2][N/2][2]  fold x pre-twiddle: Re / Im as dot products of the four samples
+  const float4* post_fwd = nullptr;  // [2][N/2]     post-twiddle x 1 / (N sqrt 2), as the two stored outputs
+  const float4* pre_inv = nullptr;   // [2][N/2]     pre-twiddle of the inverse
+  const float4* post_inv = nullptr;  // [2][N/2]     post-twiddle x 2 sqrt 2
 };
 
 // Device-resident psychoacoustic tables (psychoacoustic.py:52-69, sparse forms from tables.h).
@@ -55,6 +60,14 @@ struct PaDeviceTables {
 };
 
 void count_launch();
+int tile_sm_count();
+
+bool mdct_tile_forward_supported(int n, int channels);
+bool mdct_tile_inverse_supported(int n, int channels);
+cudaError_t mdct_forward_tile(const MdctDeviceTables& tb, const float* x, float* y, int64_t batches, int64_t blocks_n,
+                              int channels, cudaStream_t stream);
+cudaError_t mdct_inverse_tile(const MdctDeviceTables& tb, const float* y, const int32_t* q, const float* thr, float* x,
+                              int64_t batches, int64_t frames_n, int channels, cudaStream_t stream);
 
 bool mdct_has_fast_path(int n);
 cudaError_t mdct_forward(const MdctDeviceTables& tb, const float* x, float* y, int64_t batches, int64_t blocks_n,

@@ -14,6 +14,7 @@
 #include "fft_core.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace ac {
 
@@ -366,6 +367,16 @@ using Plan4096 = FftPlan<2048, 16, 16, 16, 8>;
 
 }  // namespace
 
+// AC_MDCT_LEGACY=1 routes 1- and 2-channel signals through the any-channel-count kernels of this file too
+// (A/B measurements and tests of that path)
+static bool legacy_path() {
+  static const bool legacy = [] {
+    const char* e = std::getenv("AC_MDCT_LEGACY");
+    return e != nullptr && e[0] == '1';
+  }();
+  return legacy;
+}
+
 bool mdct_has_fast_path(int n) {
   return n == 16 || n == 32 || n == 64 || n == 128 || n == 256 || n == 512 || n == 1024 || n == 2048 || n == 4096;
 }
@@ -373,6 +384,7 @@ bool mdct_has_fast_path(int n) {
 cudaError_t mdct_forward(const MdctDeviceTables& tb, const float* x, float* y, int64_t batches, int64_t blocks_n,
                          int C, cudaStream_t stream) {
   if (batches == 0) return cudaSuccess;
+  if (!legacy_path() && mdct_tile_forward_supported(tb.n, C)) return mdct_forward_tile(tb, x, y, batches, blocks_n, C, stream);
   const int bn = static_cast<int>(blocks_n);
   switch (tb.n) {
     case 16: return launch_forward<Plan16, 128>(tb, x, y, batches, bn, C, stream);
@@ -397,6 +409,8 @@ cudaError_t mdct_forward(const MdctDeviceTables& tb, const float* x, float* y, i
 cudaError_t mdct_inverse(const MdctDeviceTables& tb, const float* y, const int32_t* q, const float* thr, float* x,
                          int64_t batches, int64_t frames_n, int C, cudaStream_t stream) {
   if (batches == 0) return cudaSuccess;
+  if (!legacy_path() && mdct_tile_inverse_supported(tb.n, C))
+    return mdct_inverse_tile(tb, y, q, thr, x, batches, frames_n, C, stream);
   const int fn = static_cast<int>(frames_n);
   switch (tb.n) {
     case 16: return launch_inverse<Plan16, 128>(tb, y, q, thr, x, batches, fn, C, stream);

@@ -1,0 +1,474 @@
+// MDCT analysis / synthesis for 1 or 2 channels: tile kernels with bulk-async staging (sm_100a).
+//
+// Reference behaviour: /root/reference/audiocodec/mdctransformer.py:61-125 (transform), :127-153
+// (inverse_transform); same mathematics as mdct_kernels.cu (fold -> pre-twiddle -> N/2-point complex FFT ->
+// post-twiddle), reorganised around what bounds it on a B200: instruction issue and shared-memory wavefronts.
+//
+//   * a tile (a run of consecutive frames of one batch row) moves between HBM and shared memory with ONE
+//     cp.async.bulk each way (TMA 1-D, mbarrier completion): no load / store instructions for global data;
+//   * every thread transforms TWO sequences at once - the two channels of a stereo frame (float2 shared
+//     loads), or two adjacent frames of a mono signal - so tables, twiddles and index arithmetic are shared;
+//   * fold + pre-twiddle are one 4-term dot product per component with host-merged coefficients, the
+//     post-twiddle writes its two outputs straight into the transposed positions;
+//   * a frame's shared-memory row is reused in place: input block -> FFT exchange scratch (XOR-swizzled
+//     instead of padded) -> output frame, so a tile needs (frames + 1) rows and several CTAs fit per SM;
+//   * the groups of a half-warp alternate the order of their two strided accesses ("variant"), which puts
+//     them on complementary bank classes: the stride-2 access pattern of the DCT-IV costs no conflicts;
+//   * the FFT passes of a group synchronise with __syncwarp (a group is at most one warp for N <= 1024).
+//
+// tools/emulate_mdct_tile.py is a NumPy emulation of exactly this index arithmetic (development aid).
+#include "kernels.h"
+#include "fft_core.cuh"
+#include "async_copy.cuh"
+
+#include <algorithm>
+
+namespace ac {
+
+namespace {
+
+template <int T>
+__device__ __forceinline__ void group_sync() {
+  if constexpr (T <= 32) {
+    __syncwarp();
+  } else {
+    __syncthreads();
+  }
+}
+
+// element `a` of the thread's two sequences: the two channels of one row (C == 2) or the same element of
+// two adjacent rows (C == 1)
+template <int C, int ROW>
+__device__ __forceinline__ float2 ld2(const float* base, int a) {
+  if constexpr (C == 2) {
+    return *reinterpret_cast<const float2*>(base + 2 * a);
+  } else {
+    return make_float2(base[a], base[a + ROW]);
+  }
+}
+template <int C, int ROW>
+__device__ __forceinline__ void st2(float* base, int a, float2 v) {
+  if constexpr (C == 2) {
+    *reinterpret_cast<float2*>(base + 2 * a) = v;
+  } else {
+    base[a] = v.x;
+    base[a + ROW] = v.y;
+  }
+}
+
+template <typename Plan>
+__device__ __forceinline__ int swz(int pos) {
+  constexpr int SH = Plan::R0 == 16 ? 4 : (Plan::R0 == 8 ? 3 : (Plan::R0 == 4 ? 2 : 1));
+  return pos ^ ((pos >> SH) & 7);
+}
+
+// ---- the FFT of two sequences; exchange through `scratch` (M float4: re0, im0, re1, im1) ---------------------
+template <typename Plan, int R, int NS>
+__device__ __forceinline__ void pass_to_scratch(const float2* v0, const float2* v1, float4* scratch, int t) {
+  constexpr int E = Plan::E, T = Plan::T;
+#pragma unroll
+  for (int q = 0; q < E / R; ++q) {
+    const int j = t + T * q;
+    const int j0 = (j / NS) * NS * R + (j % NS);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      scratch[swz<Plan>(j0 + r * NS)] = make_float4(v0[q * R + r].x, v0[q * R + r].y, v1[q * R + r].x, v1[q * R + r].y);
+  }
+}
+
+template <typename Plan, int R, int NS>
+__device__ __forceinline__ void pass_from_scratch(float2* v0, float2* v1, const float4* scratch, int t,
+                                                  const float2* __restrict__ roots) {
+  constexpr int M = Plan::M, E = Plan::E, T = Plan::T;
+#pragma unroll
+  for (int q = 0; q < E / R; ++q) {
+    const int j = t + T * q;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float4 x = scratch[swz<Plan>(j + r * (M / R))];
+      v0[q * R + r] = make_float2(x.x, x.y);
+      v1[q * R + r] = make_float2(x.z, x.w);
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < E / R; ++q) {
+    const int j = t + T * q;
+    const int k = j % NS;
+#pragma unroll
+    for (int r = 1; r < R; ++r) {
+      const float2 w = __ldg(&roots[r * k * (M / (NS * R))]);
+      v0[q * R + r] = cmul(v0[q * R + r], w);
+      v1[q * R + r] = cmul(v1[q * R + r], w);
+    }
+    dft<R>(&v0[q * R]);
+    dft<R>(&v1[q * R]);
+  }
+}
+
+// On entry v0 / v1 hold the pass-0 inputs in Plan::in_index order and nobody reads `scratch` any more; on exit
+// they hold the spectra in Plan::out_index order and every read of `scratch` by this group has completed.
+template <typename Plan>
+__device__ __forceinline__ void fft2(float2* v0, float2* v1, float4* scratch, int t, const float2* __restrict__ roots) {
+  constexpr int E = Plan::E, T = Plan::T, R0 = Plan::R0, R1 = Plan::R1, R2 = Plan::R2;
+#pragma unroll
+  for (int q = 0; q < E / R0; ++q) {
+    dft<R0>(&v0[q * R0]);
+    dft<R0>(&v1[q * R0]);
+  }
+  if constexpr (R1 > 1) {
+    pass_to_scratch<Plan, R0, 1>(v0, v1, scratch, t);
+    group_sync<T>();
+    pass_from_scratch<Plan, R1, R0>(v0, v1, scratch, t, roots);
+    if constexpr (R2 > 1) {
+      group_sync<T>();
+      pass_to_scratch<Plan, R1, R0>(v0, v1, scratch, t);
+      group_sync<T>();
+      pass_from_scratch<Plan, R2, R0 * R1>(v0, v1, scratch, t, roots);
+    }
+    group_sync<T>();
+  }
+}
+
+// post-twiddle: the two outputs of spectrum bin k go to positions 2k and N-1-2k (order set by the variant)
+template <typename Plan, int C, int ROW>
+__device__ __forceinline__ void post_store(const float2* v0, const float2* v1, float* out, int t, int variant,
+                                           const float4* __restrict__ post) {
+  constexpr int M = Plan::M, N = 2 * M, E = Plan::E;
+#pragma unroll
+  for (int s = 0; s < E; ++s) {
+    const int k = Plan::out_index(t, s);
+    const float4 c4 = __ldg(&post[variant * M + k]);
+    const int i1 = variant ? N - 1 - 2 * k : 2 * k;
+    const int i2 = (N - 1) - i1;
+    st2<C, ROW>(out, i1, make_float2(fmaf(v0[s].y, c4.y, v0[s].x * c4.x), fmaf(v1[s].y, c4.y, v1[s].x * c4.x)));
+    st2<C, ROW>(out, i2, make_float2(fmaf(v0[s].y, c4.w, v0[s].x * c4.z), fmaf(v1[s].y, c4.w, v1[s].x * c4.z)));
+  }
+}
+
+template <typename Plan, int C, int THREADS>
+struct TileShape {
+  static constexpr int M = Plan::M, N = 2 * M, T = Plan::T;
+  static constexpr int G = THREADS / T;              // groups per CTA
+  static constexpr int FP = G * (2 / C);             // frames transformed per tile
+  static constexpr int ROW = N * C;                  // floats per frame / block row
+  static_assert(THREADS % T == 0 && G >= 1, "tile shape");
+};
+
+// ------------------------------------------------------------------------------------------ forward
+template <typename Plan, int C, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+mdct_forward_tile_kernel(MdctDeviceTables tb, const float* __restrict__ x, float* __restrict__ y, int blocks_n,
+                         int tiles_per_row, int64_t total_tiles) {
+  using S = TileShape<Plan, C, THREADS>;
+  constexpr int M = S::M, N = S::N, H = M, T = S::T, E = Plan::E, FP = S::FP, ROW = S::ROW, R0 = Plan::R0;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* buf = reinterpret_cast<float*>(smem_raw);                    // [FP + 1][ROW]: row r = block f0 - 1 + r
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(buf + (FP + 1) * ROW);
+
+  const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = g & 1;
+  const int frames = blocks_n + 1;
+  float* prev = buf + g * (2 / C) * ROW;      // block row before this group's (first) frame
+  float* cur = prev + ROW;                    // this group's frame row: input block, FFT scratch, output frame
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int64_t b = tile / tiles_per_row;
+    const int f0 = static_cast<int>(tile - b * tiles_per_row) * FP;
+    // rows r in [r_lo, r_hi) hold real blocks, the others are the zero padding (mdctransformer.py:366)
+    const int r_lo = f0 == 0 ? 1 : 0;
+    const int r_hi = min(FP + 1, blocks_n - f0 + 1);
+    if (r_hi > r_lo) {
+      if (tid == 0) {
+        bulk_wait_read<0>();                  // the previous tile's store has finished reading `buf`
+        const uint32_t bytes = static_cast<uint32_t>(r_hi - r_lo) * ROW * sizeof(float);
+        mbar_arrive_expect_tx(mbar, bytes);
+        bulk_load(buf + r_lo * ROW, x + (b * blocks_n + (f0 - 1 + r_lo)) * static_cast<int64_t>(ROW), bytes, mbar);
+      }
+      mbar_wait(mbar, parity);
+      parity ^= 1;
+    } else {
+      if (tid == 0) bulk_wait_read<0>();
+      __syncthreads();
+    }
+    if (r_lo > 0)
+      for (int i = tid * 4; i < ROW; i += THREADS * 4) *reinterpret_cast<float4*>(buf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r_hi < FP + 1) {
+      const int z0 = max(r_hi, r_lo) * ROW;
+      for (int i = z0 + tid * 4; i < (FP + 1) * ROW; i += THREADS * 4)
+        *reinterpret_cast<float4*>(buf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+      __syncthreads();
+    } else if (r_lo > 0) {
+      __syncthreads();
+    }
+
+    // ---- window + fold + pre-twiddle: one 4-term dot product per component        (mdctransformer.py:118, H)
+    float2 v0[E], v1[E];
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+      const int n = Plan::in_index(t, s);
+      constexpr int kHalf = R0 / 2;
+      const bool low = (s % R0) < kHalf;      // n < N/4: the pair comes from odd positions
+      const int p = low ? H - 1 - 2 * n : 2 * n - H;
+      const int a1 = variant ? N - 1 - p : p;
+      const int a2 = (N - 1) - a1;
+      const float2 l0 = ld2<C, ROW>(prev, a1), l1 = ld2<C, ROW>(prev, a2);
+      const float2 l2 = ld2<C, ROW>(cur, a1), l3 = ld2<C, ROW>(cur, a2);
+      const float4 kr = __ldg(&tb.pre_fwd[(variant * M + n) * 2]);
+      const float4 ki = __ldg(&tb.pre_fwd[(variant * M + n) * 2 + 1]);
+      v0[s].x = fmaf(l3.x, kr.w, fmaf(l2.x, kr.z, fmaf(l1.x, kr.y, l0.x * kr.x)));
+      v0[s].y = fmaf(l3.x, ki.w, fmaf(l2.x, ki.z, fmaf(l1.x, ki.y, l0.x * ki.x)));
+      v1[s].x = fmaf(l3.y, kr.w, fmaf(l2.y, kr.z, fmaf(l1.y, kr.y, l0.y * kr.x)));
+      v1[s].y = fmaf(l3.y, ki.w, fmaf(l2.y, ki.z, fmaf(l1.y, ki.y, l0.y * ki.x)));
+    }
+    __syncthreads();                          // every block row has been read: rows become scratch / output
+
+    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(cur), t, tb.roots);
+    post_store<Plan, C, ROW>(v0, v1, cur, t, variant, tb.post_fwd);
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      const int nf = min(FP, frames - f0);
+      bulk_store(y + (b * frames + f0) * static_cast<int64_t>(ROW), buf + ROW, static_cast<uint32_t>(nf) * ROW * sizeof(float));
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------ inverse
+// A tile transforms FP consecutive frames (the first one is the halo: frame nb0 - 1) and emits the FP - 1
+// output blocks nb0 .. nb0 + FP - 2, each of which needs two adjacent frames (TDAC overlap-add, H_inv).
+template <typename Plan, int C, int THREADS, int MINB, bool DEQUANT>
+__global__ void __launch_bounds__(THREADS, MINB)
+mdct_inverse_tile_kernel(MdctDeviceTables tb, const float* __restrict__ y, const int32_t* __restrict__ q,
+                         const float* __restrict__ thr, float* __restrict__ x, int frames_n, int tiles_per_row,
+                         int64_t total_tiles) {
+  using S = TileShape<Plan, C, THREADS>;
+  constexpr int M = S::M, N = S::N, H = M, T = S::T, E = Plan::E, FP = S::FP, ROW = S::ROW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* abuf = reinterpret_cast<float*>(smem_raw);      // [FP][ROW]: amplitudes / steps -> scratch -> v = sqrt(4N) DCT-IV
+  float* bbuf = abuf + FP * ROW;                         // [FP][ROW]: quantised integers -> output blocks
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(bbuf + FP * ROW);
+
+  const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = g & 1;
+  float* arow = abuf + g * (2 / C) * ROW;
+  const int32_t* qrow = reinterpret_cast<const int32_t*>(bbuf) + g * (2 / C) * ROW;
+  if (tid == 0) {
+    mbar_init(mbar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int64_t b = tile / tiles_per_row;
+    const int nb0 = static_cast<int>(tile - b * tiles_per_row) * (FP - 1);   // first output block
+    const int fs = nb0 - 1;                                                   // first frame of the tile
+    const int r_lo = fs < 0 ? 1 : 0;
+    const int r_hi = min(FP, frames_n - fs);
+    if (r_hi > r_lo) {
+      if (tid == 0) {
+        bulk_wait_read<0>();
+        const uint32_t bytes = static_cast<uint32_t>(r_hi - r_lo) * ROW * sizeof(float);
+        const int64_t off = (b * frames_n + (fs + r_lo)) * static_cast<int64_t>(ROW);
+        if (DEQUANT) {
+          mbar_arrive_expect_tx(mbar, 2 * bytes);
+          bulk_load(abuf + r_lo * ROW, thr + off, bytes, mbar);
+          bulk_load(bbuf + r_lo * ROW, q + off, bytes, mbar);
+        } else {
+          mbar_arrive_expect_tx(mbar, bytes);
+          bulk_load(abuf + r_lo * ROW, y + off, bytes, mbar);
+        }
+      }
+      mbar_wait(mbar, parity);
+      parity ^= 1;
+    } else {
+      if (tid == 0) bulk_wait_read<0>();
+      __syncthreads();
+    }
+    if (r_lo > 0 || r_hi < FP) {               // frames outside the signal are zero (mdctransformer.py:366)
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r_lo > 0)
+        for (int i = tid * 4; i < ROW; i += THREADS * 4) {
+          *reinterpret_cast<float4*>(abuf + i) = z;
+          if (DEQUANT) *reinterpret_cast<float4*>(bbuf + i) = z;
+        }
+      const int z0 = max(r_hi, r_lo) * ROW;
+      for (int i = z0 + tid * 4; i < FP * ROW; i += THREADS * 4) {
+        *reinterpret_cast<float4*>(abuf + i) = z;
+        if (DEQUANT) *reinterpret_cast<float4*>(bbuf + i) = z;
+      }
+      __syncthreads();
+    }
+
+    // ---- (dequantise,) pre-twiddle                                                 (mdctransformer.py:141-148)
+    float2 v0[E], v1[E];
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+      const int n = Plan::in_index(t, s);
+      const int a1 = variant ? N - 1 - 2 * n : 2 * n;
+      const int a2 = (N - 1) - a1;
+      float2 l1 = ld2<C, ROW>(arow, a1), l2 = ld2<C, ROW>(arow, a2);
+      if (DEQUANT) {
+        const float2 q1 = ld2<C, ROW>(reinterpret_cast<const float*>(qrow), a1);
+        const float2 q2 = ld2<C, ROW>(reinterpret_cast<const float*>(qrow), a2);
+        l1.x *= static_cast<float>(__float_as_int(q1.x));
+        l1.y *= static_cast<float>(__float_as_int(q1.y));
+        l2.x *= static_cast<float>(__float_as_int(q2.x));
+        l2.y *= static_cast<float>(__float_as_int(q2.y));
+      }
+      const float4 k4 = __ldg(&tb.pre_inv[variant * M + n]);
+      v0[s] = make_float2(fmaf(l2.x, k4.y, l1.x * k4.x), fmaf(l2.x, k4.w, l1.x * k4.z));
+      v1[s] = make_float2(fmaf(l2.y, k4.y, l1.y * k4.x), fmaf(l2.y, k4.w, l1.y * k4.z));
+    }
+    group_sync<T>();                           // the group's rows have been read: they become its scratch
+
+    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(arow), t, tb.roots);
+    post_store<Plan, C, ROW>(v0, v1, arow, t, variant, tb.post_inv);
+    __syncthreads();
+
+    // ---- synthesis window + TDAC overlap-add (H_inv, mdctransformer.py:148,176-190): block i of the tile takes
+    //      the lower half of v of frame i + 1 and the upper half of v of frame i
+    constexpr int PAIRS = (FP - 1) * H;
+    for (int idx = tid; idx < PAIRS; idx += THREADS) {
+      const int bl = idx / H, p = idx % H;
+      const float4 s = __ldg(&tb.unfold[p]);
+      const float* vn = abuf + (bl + 1) * ROW + (H - 1 - p) * C;
+      const float* vp = abuf + bl * ROW + (H + p) * C;
+      float* xo = bbuf + bl * ROW;
+      if constexpr (C == 2) {
+        const float2 a = *reinterpret_cast<const float2*>(vn), c = *reinterpret_cast<const float2*>(vp);
+        *reinterpret_cast<float2*>(xo + 2 * p) = make_float2(fmaf(s.x, a.x, s.y * c.x), fmaf(s.x, a.y, s.y * c.y));
+        *reinterpret_cast<float2*>(xo + 2 * (N - 1 - p)) = make_float2(fmaf(s.z, a.x, s.w * c.x), fmaf(s.z, a.y, s.w * c.y));
+      } else {
+        xo[p] = fmaf(s.x, vn[0], s.y * vp[0]);
+        xo[N - 1 - p] = fmaf(s.z, vn[0], s.w * vp[0]);
+      }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+      const int nblk = min(FP - 1, frames_n + 1 - nb0);
+      bulk_store(x + (b * (frames_n + 1) + nb0) * static_cast<int64_t>(ROW), bbuf, static_cast<uint32_t>(nblk) * ROW * sizeof(float));
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+template <typename Plan, int C, int THREADS, int MINB>
+cudaError_t launch_forward_tile(const MdctDeviceTables& tb, const float* x, float* y, int64_t batches, int blocks_n,
+                                cudaStream_t stream) {
+  using S = TileShape<Plan, C, THREADS>;
+  const size_t smem = static_cast<size_t>(S::FP + 1) * S::ROW * sizeof(float) + 16;
+  auto kernel = mdct_forward_tile_kernel<Plan, C, THREADS, MINB>;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  const int tiles_per_row = (blocks_n + 1 + S::FP - 1) / S::FP;
+  const int64_t total = batches * tiles_per_row;
+  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  per_sm = std::max(1, std::min(per_sm, MINB));
+  const int64_t cap = static_cast<int64_t>(tile_sm_count()) * per_sm;
+  kernel<<<static_cast<unsigned>(std::min(total, cap)), THREADS, smem, stream>>>(tb, x, y, blocks_n, tiles_per_row, total);
+  count_launch();
+  return cudaGetLastError();
+}
+
+template <typename Plan, int C, int THREADS, int MINB>
+cudaError_t launch_inverse_tile(const MdctDeviceTables& tb, const float* y, const int32_t* q, const float* thr, float* x,
+                                int64_t batches, int frames_n, cudaStream_t stream) {
+  using S = TileShape<Plan, C, THREADS>;
+  static_assert(S::FP >= 2, "an inverse tile needs two frames");
+  const size_t smem = static_cast<size_t>(2 * S::FP) * S::ROW * sizeof(float) + 16;
+  const int tiles_per_row = (frames_n + 1 + S::FP - 2) / (S::FP - 1);
+  const int64_t total = batches * tiles_per_row;
+  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  per_sm = std::max(1, std::min(per_sm, MINB));
+  const int64_t cap = static_cast<int64_t>(tile_sm_count()) * per_sm;
+  const unsigned grid = static_cast<unsigned>(std::min(total, cap));
+  cudaError_t err;
+  if (q != nullptr) {
+    auto kernel = mdct_inverse_tile_kernel<Plan, C, THREADS, MINB, true>;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    kernel<<<grid, THREADS, smem, stream>>>(tb, y, q, thr, x, frames_n, tiles_per_row, total);
+  } else {
+    auto kernel = mdct_inverse_tile_kernel<Plan, C, THREADS, MINB, false>;
+    err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
+    kernel<<<grid, THREADS, smem, stream>>>(tb, y, q, thr, x, frames_n, tiles_per_row, total);
+  }
+  count_launch();
+  return cudaGetLastError();
+}
+
+//                       M    E  R0  R1 R2
+using Plan64 = FftPlan<32, 8, 8, 4, 1>;
+using Plan128 = FftPlan<64, 8, 8, 8, 1>;
+using Plan256 = FftPlan<128, 16, 16, 8, 1>;
+using Plan512 = FftPlan<256, 16, 16, 16, 1>;
+using Plan1024 = FftPlan<512, 16, 8, 8, 8>;
+
+}  // namespace
+
+int tile_sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+      cached = sms;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+bool mdct_tile_forward_supported(int n, int channels) {
+  return (channels == 1 || channels == 2) && (n == 64 || n == 128 || n == 256 || n == 512 || n == 1024);
+}
+
+bool mdct_tile_inverse_supported(int n, int channels) {
+  return (channels == 1 || channels == 2) && (n == 64 || n == 128 || n == 256 || n == 512);
+}
+
+cudaError_t mdct_forward_tile(const MdctDeviceTables& tb, const float* x, float* y, int64_t batches, int64_t blocks_n,
+                              int C, cudaStream_t stream) {
+  const int bn = static_cast<int>(blocks_n);
+#define AC_FWD(PLAN, THREADS, MINB)                                                                   \
+  return C == 2 ? launch_forward_tile<PLAN, 2, THREADS, MINB>(tb, x, y, batches, bn, stream)         \
+                : launch_forward_tile<PLAN, 1, THREADS, MINB>(tb, x, y, batches, bn, stream)
+  switch (tb.n) {
+    case 64: AC_FWD(Plan64, 128, 4);
+    case 128: AC_FWD(Plan128, 128, 4);
+    case 256: AC_FWD(Plan256, 128, 3);
+    case 512: AC_FWD(Plan512, 128, 3);
+    case 1024: AC_FWD(Plan1024, 256, 1);
+    default: return cudaErrorInvalidConfiguration;
+  }
+#undef AC_FWD
+}
+
+cudaError_t mdct_inverse_tile(const MdctDeviceTables& tb, const float* y, const int32_t* q, const float* thr, float* x,
+                              int64_t batches, int64_t frames_n, int C, cudaStream_t stream) {
+  const int fn = static_cast<int>(frames_n);
+#define AC_INV(PLAN, THREADS, MINB)                                                                          \
+  return C == 2 ? launch_inverse_tile<PLAN, 2, THREADS, MINB>(tb, y, q, thr, x, batches, fn, stream)        \
+                : launch_inverse_tile<PLAN, 1, THREADS, MINB>(tb, y, q, thr, x, batches, fn, stream)
+  switch (tb.n) {
+    case 64: AC_INV(Plan64, 128, 4);
+    case 128: AC_INV(Plan128, 128, 4);
+    case 256: AC_INV(Plan256, 128, 3);
+    case 512: AC_INV(Plan512, 128, 3);
+    default: return cudaErrorInvalidConfiguration;
+  }
+#undef AC_INV
+}
+
+}  // namespace ac

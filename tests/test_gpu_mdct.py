@@ -142,9 +142,10 @@ def test_full_size_round_trip_cfg2():
   back = mdct.inverse_transform(y)
   err = (back[:, n:-n] - x).abs().max().item()
   assert err < 1e-5, err
-  # TDAC with a power-complementary window is orthogonal: energy is conserved up to the 1/(2N) scale
+  # the fold with a power-complementary window and the DCT-IV are orthogonal, the transform then scales by
+  # 1 / sqrt(4N) (mdctransformer.py:125): energy is conserved up to the factor 4N
   e_x = x.double().pow(2).sum().item()
-  e_y = y.double().pow(2).sum().item() * 2 * n
+  e_y = y.double().pow(2).sum().item() * 4 * n
   assert abs(e_y / e_x - 1) < 1e-4
   # linearity
   y2 = mdct.transform(0.5 * x)
