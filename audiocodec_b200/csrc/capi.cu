@@ -349,8 +349,9 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
   d.max_band_cnt = t.max_band_cnt;
   d.max_filt_cnt = t.max_filt_cnt;
   d.gain_log2 = static_cast<float>(-alpha * std::log2(10.0) / 10.0);
-  // ---- tile-kernel tables: chunks of 256 filters; in every chunk the bands are split four ways by cost
-  d.chunk_k = 256;
+  // ---- tile-kernel tables: chunks of chunk_k filters; a chunk's band sums are cut into steps of four filters
+  //      and the steps dealt to the four warps of a CTA in contiguous, equally long runs
+  d.chunk_k = 128;
   d.n_chunks = (t.n + d.chunk_k - 1) / d.chunk_k;
   d.tile_ok = (t.nb == 64 && t.max_filt_cnt <= 3) ? 1 : 0;
   std::vector<int4> band_desc;
@@ -358,35 +359,39 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
   std::vector<int32_t> desc_start(static_cast<size_t>(d.n_chunks) * 5 + 1, 0);
   for (int c = 0; c < d.n_chunks; ++c) {
     const int kc0 = c * d.chunk_k, kc1 = std::min(t.n, kc0 + d.chunk_k);
-    std::vector<int> bands;
+    const size_t first_desc = band_desc.size();
     std::vector<double> cost;
-    double total = 0;
     for (int i = 0; i < t.nb; ++i) {
       const int ka = std::max(t.band_k0[i], kc0), kb = std::min(t.band_k0[i] + t.band_cnt[i], kc1);
-      if (kb > ka) {
-        bands.push_back(i);
-        const bool final = t.band_k0[i] + t.band_cnt[i] <= kc1;
-        cost.push_back(12.0 + 12.0 * ((kb - ka + 3) / 4) + (final ? 24.0 : 0.0));   // ~instructions per lane
-        total += cost.back();
+      if (kb <= ka) continue;
+      const int steps = (kb - ka + 3) / 4;
+      const bool final = t.band_k0[i] + t.band_cnt[i] <= kc1;
+      for (int st = 0; st < steps; ++st) {
+        int4 ds;
+        ds.x = ka - kc0 + 4 * st;                        // row of T
+        ds.y = static_cast<int>(band_w4.size());         // four weights
+        ds.z = i | (t.band_k0[i] < kc0 ? 0x100 : 0) | (final ? 0x200 : 0) | (st == 0 ? 0x400 : 0) |
+               (st == steps - 1 ? 0x800 : 0);
+        ds.w = 0;
+        for (int u = 0; u < 4; ++u) {
+          const int k = ka + 4 * st + u;
+          band_w4.push_back(k < kb ? t.band_w[t.band_ptr[i] + (k - t.band_k0[i])] : 0.f);
+        }
+        band_desc.push_back(ds);
+        cost.push_back(14.0 + (st == steps - 1 ? (final ? 30.0 : 6.0) : 0.0));   // ~instructions per lane
       }
     }
+    // contiguous runs of about equal cost; a band's steps stay with one warp (the accumulator is a register)
+    double total = 0;
+    for (double v : cost) total += v;
     double run = 0;
     int w = 0;
-    desc_start[static_cast<size_t>(c) * 5] = static_cast<int32_t>(band_desc.size());
-    for (size_t b = 0; b < bands.size(); ++b) {
-      const int i = bands[b];
-      const int ka = std::max(t.band_k0[i], kc0), kb = std::min(t.band_k0[i] + t.band_cnt[i], kc1);
-      const int steps = (kb - ka + 3) / 4;
-      int4 ds;
-      ds.x = ka - kc0;
-      ds.y = steps;
-      ds.z = static_cast<int>(band_w4.size());
-      ds.w = i | (t.band_k0[i] < kc0 ? 0x100 : 0) | (t.band_k0[i] + t.band_cnt[i] <= kc1 ? 0x200 : 0);
-      for (int s = 0; s < 4 * steps; ++s)
-        band_w4.push_back(ka + s < kb ? t.band_w[t.band_ptr[i] + (ka + s - t.band_k0[i])] : 0.f);
-      band_desc.push_back(ds);
-      run += cost[b];
-      while (w < 3 && run >= total * (w + 1) / 4.0) desc_start[static_cast<size_t>(c) * 5 + (++w)] = static_cast<int32_t>(band_desc.size());
+    desc_start[static_cast<size_t>(c) * 5] = static_cast<int32_t>(first_desc);
+    for (size_t sidx = 0; sidx < cost.size(); ++sidx) {
+      run += cost[sidx];
+      const bool band_end = (band_desc[first_desc + sidx].z & 0x800) != 0;
+      while (band_end && w < 3 && run >= total * (w + 1) / 4.0)
+        desc_start[static_cast<size_t>(c) * 5 + (++w)] = static_cast<int32_t>(first_desc + sidx + 1);
     }
     while (w < 4) desc_start[static_cast<size_t>(c) * 5 + (++w)] = static_cast<int32_t>(band_desc.size());
   }

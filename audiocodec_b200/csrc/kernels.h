@@ -46,9 +46,10 @@ struct PaDeviceTables {
   const float* spread_fn = nullptr;   // [2 nb]
   const float* lin = nullptr;         // [nb]
   // tile kernel (nb == 64, <= 3 bands per filter): the filter axis is processed in chunks of chunk_k filters.
-  //   band_desc[d] = { row of the band's first filter inside the chunk, number of 4-filter steps,
-  //                    offset into band_w4 (zero-padded to whole steps), band | add-partial << 8 | final << 9 }
-  //   desc_start[5 c + w] .. desc_start[5 c + w + 1]: the descriptors warp w of a 4-warp CTA sums in chunk c
+  //   band_desc[d] = one step of four filters of a band sum: { row of T, offset of its four (zero-padded)
+  //                  weights in band_w4, band | add-earlier-partial << 8 | band-complete << 9 | first-step << 10 |
+  //                  last-step-in-chunk << 11, 0 }
+  //   desc_start[5 c + w] .. desc_start[5 c + w + 1]: the steps warp w of a 4-warp CTA runs in chunk c
   //   filt4[k] = { w0, w1, w2, first band (as int bits) }: W_inv weights of the three bands from `first band`
   int chunk_k = 0, n_chunks = 0, tile_ok = 0;
   int n_desc = 0, n_band_w4 = 0;
