@@ -314,13 +314,10 @@ def run_b200_arm(args):
     sampler.stop()
 
   # ---- aggregate over ranks: max time, gathered bitstream statistics ---------------------------------
-  times = torch.tensor([total_ms, e2e_ms], device=device, dtype=torch.float64)
-  stats = codec.stats(q).to(torch.float64)
-  if world > 1:
-    dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    gathered = [torch.empty_like(stats) for _ in range(world)]
-    dist.all_gather(gathered, stats)          # the one collective of the job: bitstream sizes and stats
-    stats = torch.stack(gathered).sum(0)
+  from audiocodec_b200 import sharding
+  times = sharding.max_over_ranks(torch.tensor([total_ms, e2e_ms], device=device, dtype=torch.float64))
+  # the one collective of the job: bitstream sizes and statistics of every shard
+  stats = sharding.gather_stats(codec.stats(q).to(torch.float64)).sum(0)
   total_ms, e2e_ms = times.tolist()
   ok = bool(torch.isfinite(xhat).all().item())
   err = (xhat[:, n:-n] - x).float().pow(2).mean().sqrt().item()
