@@ -155,54 +155,60 @@ struct TileShape {
 };
 
 // ------------------------------------------------------------------------------------------ forward
+// Two tile buffers: the bulk load of tile i + 1 is in flight while tile i is transformed.
 template <typename Plan, int C, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
 mdct_forward_tile_kernel(MdctDeviceTables tb, const float* __restrict__ x, float* __restrict__ y, int blocks_n,
                          int tiles_per_row, int64_t total_tiles) {
   using S = TileShape<Plan, C, THREADS>;
   constexpr int M = S::M, N = S::N, H = M, T = S::T, E = Plan::E, FP = S::FP, ROW = S::ROW, R0 = Plan::R0;
+  constexpr int BUF = (FP + 1) * ROW;                                 // floats per tile buffer
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* buf = reinterpret_cast<float*>(smem_raw);                    // [FP + 1][ROW]: row r = block f0 - 1 + r
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(buf + (FP + 1) * ROW);
+  float* bufs = reinterpret_cast<float*>(smem_raw);                   // [2][FP + 1][ROW]: row r = block f0 - 1 + r
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(bufs + 2 * BUF);       // [2]
 
   const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = g & 1;
   const int frames = blocks_n + 1;
-  float* prev = buf + g * (2 / C) * ROW;      // block row before this group's (first) frame
-  float* cur = prev + ROW;                    // this group's frame row: input block, FFT scratch, output frame
   if (tid == 0) {
-    mbar_init(mbar, 1);
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  uint32_t parity = 0;
 
-  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  // rows r in [r_lo, r_hi) of a tile hold real blocks, the others are the zero padding (mdctransformer.py:366)
+  auto issue_load = [&](int64_t tile, int slot) {        // thread 0 only
     const int64_t b = tile / tiles_per_row;
     const int f0 = static_cast<int>(tile - b * tiles_per_row) * FP;
-    // rows r in [r_lo, r_hi) hold real blocks, the others are the zero padding (mdctransformer.py:366)
     const int r_lo = f0 == 0 ? 1 : 0;
     const int r_hi = min(FP + 1, blocks_n - f0 + 1);
     if (r_hi > r_lo) {
-      if (tid == 0) {
-        bulk_wait_read<0>();                  // the previous tile's store has finished reading `buf`
-        const uint32_t bytes = static_cast<uint32_t>(r_hi - r_lo) * ROW * sizeof(float);
-        mbar_arrive_expect_tx(mbar, bytes);
-        bulk_load(buf + r_lo * ROW, x + (b * blocks_n + (f0 - 1 + r_lo)) * static_cast<int64_t>(ROW), bytes, mbar);
-      }
-      mbar_wait(mbar, parity);
-      parity ^= 1;
+      const uint32_t bytes = static_cast<uint32_t>(r_hi - r_lo) * ROW * sizeof(float);
+      mbar_arrive_expect_tx(&mbar[slot], bytes);
+      bulk_load(bufs + slot * BUF + r_lo * ROW, x + (b * blocks_n + (f0 - 1 + r_lo)) * static_cast<int64_t>(ROW), bytes,
+                &mbar[slot]);
     } else {
-      if (tid == 0) bulk_wait_read<0>();
-      __syncthreads();
+      mbar_arrive(&mbar[slot]);
     }
-    if (r_lo > 0)
-      for (int i = tid * 4; i < ROW; i += THREADS * 4) *reinterpret_cast<float4*>(buf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r_hi < FP + 1) {
-      const int z0 = max(r_hi, r_lo) * ROW;
-      for (int i = z0 + tid * 4; i < (FP + 1) * ROW; i += THREADS * 4)
-        *reinterpret_cast<float4*>(buf + i) = make_float4(0.f, 0.f, 0.f, 0.f);
-      __syncthreads();
-    } else if (r_lo > 0) {
+  };
+  if (tid == 0 && blockIdx.x < total_tiles) issue_load(blockIdx.x, 0);
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int slot = it & 1;
+    float* buf = bufs + slot * BUF;
+    float* prev = buf + g * (2 / C) * ROW;      // block row before this group's (first) frame
+    float* cur = prev + ROW;                    // this group's frame row: input block, FFT scratch, output frame
+    const int64_t b = tile / tiles_per_row;
+    const int f0 = static_cast<int>(tile - b * tiles_per_row) * FP;
+    const int r_lo = f0 == 0 ? 1 : 0;
+    const int r_hi = min(FP + 1, blocks_n - f0 + 1);
+    mbar_wait(&mbar[slot], (it >> 1) & 1);
+    if (r_lo > 0 || r_hi < FP + 1) {
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r_lo > 0)
+        for (int i = tid * 4; i < ROW; i += THREADS * 4) *reinterpret_cast<float4*>(buf + i) = z;
+      for (int i = max(r_hi, r_lo) * ROW + tid * 4; i < BUF; i += THREADS * 4) *reinterpret_cast<float4*>(buf + i) = z;
       __syncthreads();
     }
 
@@ -226,6 +232,10 @@ mdct_forward_tile_kernel(MdctDeviceTables tb, const float* __restrict__ x, float
       v1[s].y = fmaf(l3.y, ki.w, fmaf(l2.y, ki.z, fmaf(l1.y, ki.y, l0.y * ki.x)));
     }
     __syncthreads();                          // every block row has been read: rows become scratch / output
+    if (tid == 0 && tile + gridDim.x < total_tiles) {
+      bulk_wait_read<0>();                    // the store that last read the other buffer has drained it
+      issue_load(tile + gridDim.x, slot ^ 1);
+    }
 
     fft2<Plan>(v0, v1, reinterpret_cast<float4*>(cur), t, tb.roots);
     post_store<Plan, C, ROW>(v0, v1, cur, t, variant, tb.post_fwd);
@@ -366,7 +376,7 @@ template <typename Plan, int C, int THREADS, int MINB>
 cudaError_t launch_forward_tile(const MdctDeviceTables& tb, const float* x, float* y, int64_t batches, int blocks_n,
                                 cudaStream_t stream) {
   using S = TileShape<Plan, C, THREADS>;
-  const size_t smem = static_cast<size_t>(S::FP + 1) * S::ROW * sizeof(float) + 16;
+  const size_t smem = static_cast<size_t>(2 * (S::FP + 1)) * S::ROW * sizeof(float) + 16;
   auto kernel = mdct_forward_tile_kernel<Plan, C, THREADS, MINB>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
