@@ -43,6 +43,11 @@ SIGNATURES = {
   "ac_pa_add_noise_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, ctypes.c_uint64, _c_void_p]),
   "ac_quantize_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
   "ac_dequantize_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
+  "ac_codec_pipeline_create": (ctypes.c_int, [_c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int,
+                                              ctypes.POINTER(_c_void_p)]),
+  "ac_codec_pipeline_destroy": (ctypes.c_int, [_c_void_p]),
+  "ac_codec_roundtrip_host_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, ctypes.c_float,
+                                                 ctypes.c_float, _c_double_p, _c_void_p]),
   "ac_mdct_forward_dl": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p]),
   "ac_mdct_inverse_dl": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p]),
   "ac_pa_tonality_dl": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p]),

@@ -494,6 +494,157 @@ int ac_dequantize_f32(const int32_t* q, const float* thr, float* y, int64_t n, v
   return err == cudaSuccess ? AC_OK : cuda_fail(err, "dequantize launch");
 }
 
+// --------------------------------------------------------------------------------- host-buffer streaming
+namespace {
+constexpr int kPipeSlots = 3;
+struct PipeSlot {
+  float *x = nullptr, *y = nullptr, *step = nullptr, *xhat = nullptr;
+  int32_t* q = nullptr;
+  cudaEvent_t x_ready = nullptr, x_free = nullptr, out_ready = nullptr, out_free = nullptr;
+};
+}  // namespace
+
+struct ac_codec_pipeline {
+  const ac_mdct_plan* mdct = nullptr;
+  const ac_pa_plan* pa = nullptr;
+  int64_t chunk_clips = 0, samples = 0;
+  int channels = 0, device = 0;
+  cudaStream_t h2d = nullptr, run = nullptr, d2h = nullptr;
+  cudaEvent_t entry = nullptr, done = nullptr;
+  PipeSlot slots[kPipeSlots];
+  unsigned long long* stats_dev = nullptr;   // [3] coefficients, non-zeros, fixed-point sum of log2(2|q|+1)
+};
+
+int ac_codec_pipeline_destroy(ac_codec_pipeline* p) {
+  if (p == nullptr) return AC_OK;
+  for (PipeSlot& s : p->slots) {
+    cudaFree(s.x);
+    cudaFree(s.y);
+    cudaFree(s.step);
+    cudaFree(s.xhat);
+    cudaFree(s.q);
+    if (s.x_ready) cudaEventDestroy(s.x_ready);
+    if (s.x_free) cudaEventDestroy(s.x_free);
+    if (s.out_ready) cudaEventDestroy(s.out_ready);
+    if (s.out_free) cudaEventDestroy(s.out_free);
+  }
+  cudaFree(p->stats_dev);
+  if (p->entry) cudaEventDestroy(p->entry);
+  if (p->done) cudaEventDestroy(p->done);
+  if (p->h2d) cudaStreamDestroy(p->h2d);
+  if (p->run) cudaStreamDestroy(p->run);
+  if (p->d2h) cudaStreamDestroy(p->d2h);
+  delete p;
+  return AC_OK;
+}
+
+int ac_codec_pipeline_create(const ac_mdct_plan* mdct, const ac_pa_plan* pa, int64_t chunk_clips, int64_t samples,
+                             int channels, ac_codec_pipeline** out) {
+  if (out == nullptr) return fail(AC_ERR_INVALID, "out is null");
+  *out = nullptr;
+  if (mdct == nullptr || pa == nullptr) return fail(AC_ERR_INVALID, "plan is null");
+  if (chunk_clips < 1 || samples < 0 || channels < 1) return fail(AC_ERR_INVALID, "invalid pipeline shape");
+  const int n = mdct->tb.n;
+  if (pa->tb.n != n) return fail(AC_ERR_INVALID, "filter_bands_n (%d) != filters_n (%d)", pa->tb.n, n);
+  if (samples % n != 0)
+    return fail(AC_ERR_INVALID, "samples_n (%lld) must be a multiple of filters_n (%d)", (long long)samples, n);
+  ac_codec_pipeline* p = new (std::nothrow) ac_codec_pipeline();
+  if (p == nullptr) return fail(AC_ERR_ALLOC, "out of host memory");
+  p->mdct = mdct;
+  p->pa = pa;
+  p->chunk_clips = chunk_clips;
+  p->samples = samples;
+  p->channels = channels;
+  const size_t frames = static_cast<size_t>(samples / n + 1);
+  const size_t in_elems = static_cast<size_t>(chunk_clips) * samples * channels;
+  const size_t amp_elems = static_cast<size_t>(chunk_clips) * frames * n * channels;
+  const size_t out_elems = static_cast<size_t>(chunk_clips) * (frames + 1) * n * channels;
+  cudaError_t err = cudaGetDevice(&p->device);
+  auto ok = [&](cudaError_t e) {
+    if (err == cudaSuccess) err = e;
+    return err == cudaSuccess;
+  };
+  ok(cudaStreamCreateWithFlags(&p->h2d, cudaStreamNonBlocking));
+  ok(cudaStreamCreateWithFlags(&p->run, cudaStreamNonBlocking));
+  ok(cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking));
+  ok(cudaEventCreateWithFlags(&p->entry, cudaEventDisableTiming));
+  ok(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
+  ok(cudaMalloc(reinterpret_cast<void**>(&p->stats_dev), 3 * sizeof(unsigned long long)));
+  for (PipeSlot& s : p->slots) {
+    ok(cudaMalloc(reinterpret_cast<void**>(&s.x), std::max<size_t>(in_elems, 4) * sizeof(float)));
+    ok(cudaMalloc(reinterpret_cast<void**>(&s.y), amp_elems * sizeof(float)));
+    ok(cudaMalloc(reinterpret_cast<void**>(&s.step), amp_elems * sizeof(float)));
+    ok(cudaMalloc(reinterpret_cast<void**>(&s.q), amp_elems * sizeof(int32_t)));
+    ok(cudaMalloc(reinterpret_cast<void**>(&s.xhat), out_elems * sizeof(float)));
+    ok(cudaEventCreateWithFlags(&s.x_ready, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&s.x_free, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&s.out_ready, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&s.out_free, cudaEventDisableTiming));
+  }
+  if (err != cudaSuccess) {
+    ac_codec_pipeline_destroy(p);
+    return cuda_fail(err, "creating the streaming pipeline");
+  }
+  *out = p;
+  return AC_OK;
+}
+
+int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float* xhat_host, int64_t batches, float drown,
+                                float thr_scale, double* stats, void* stream) {
+  if (p == nullptr) return fail(AC_ERR_INVALID, "pipeline is null");
+  if (batches < 0) return fail(AC_ERR_INVALID, "negative batch");
+  if (!(thr_scale > 0.f)) return fail(AC_ERR_INVALID, "thr_scale must be positive");
+  if (batches > 0 && (x_host == nullptr || xhat_host == nullptr)) return fail(AC_ERR_INVALID, "null host buffer");
+  const int n = p->mdct->tb.n, c = p->channels;
+  const int64_t s = p->samples, blocks = s / n, frames = blocks + 1;
+  const size_t in_clip = static_cast<size_t>(s) * c, out_clip = static_cast<size_t>(frames + 1) * n * c;
+  cudaError_t err = cudaSuccess;
+  auto ok = [&](cudaError_t e) {
+    if (err == cudaSuccess) err = e;
+    return err == cudaSuccess;
+  };
+  cudaStream_t caller = static_cast<cudaStream_t>(stream);
+  ok(cudaEventRecord(p->entry, caller));
+  ok(cudaStreamWaitEvent(p->h2d, p->entry, 0));
+  ok(cudaStreamWaitEvent(p->run, p->entry, 0));
+  ok(cudaStreamWaitEvent(p->d2h, p->entry, 0));
+  if (stats != nullptr) ok(cudaMemsetAsync(p->stats_dev, 0, 3 * sizeof(unsigned long long), p->run));
+  int k = 0;
+  for (int64_t i = 0; i < batches && err == cudaSuccess; i += p->chunk_clips, ++k) {
+    const int64_t cb = std::min(p->chunk_clips, batches - i);
+    PipeSlot& sl = p->slots[k % kPipeSlots];
+    if (k >= kPipeSlots) ok(cudaStreamWaitEvent(p->h2d, sl.x_free, 0));
+    if (in_clip > 0) ok(cudaMemcpyAsync(sl.x, x_host + i * in_clip, cb * in_clip * sizeof(float), cudaMemcpyHostToDevice, p->h2d));
+    ok(cudaEventRecord(sl.x_ready, p->h2d));
+    ok(cudaStreamWaitEvent(p->run, sl.x_ready, 0));
+    ok(ac::mdct_forward(p->mdct->tb, sl.x, sl.y, cb, blocks, c, p->run));
+    ok(cudaEventRecord(sl.x_free, p->run));
+    ok(ac::pa_threshold(p->pa->tb, sl.y, nullptr, drown, thr_scale, sl.step, sl.q, cb * frames, c, p->run));
+    if (stats != nullptr) ok(ac::codec_stats(sl.q, cb * frames * n * c, p->stats_dev, p->run));
+    if (k >= kPipeSlots) ok(cudaStreamWaitEvent(p->run, sl.out_free, 0));
+    ok(ac::mdct_inverse(p->mdct->tb, nullptr, sl.q, sl.step, sl.xhat, cb, frames, c, p->run));
+    ok(cudaEventRecord(sl.out_ready, p->run));
+    ok(cudaStreamWaitEvent(p->d2h, sl.out_ready, 0));
+    ok(cudaMemcpyAsync(xhat_host + i * out_clip, sl.xhat, cb * out_clip * sizeof(float), cudaMemcpyDeviceToHost, p->d2h));
+    ok(cudaEventRecord(sl.out_free, p->d2h));
+  }
+  unsigned long long host_stats[3] = {0, 0, 0};
+  if (stats != nullptr) {
+    ok(cudaStreamWaitEvent(p->d2h, p->slots[(k + kPipeSlots - 1) % kPipeSlots].out_ready, 0));
+    ok(cudaMemcpyAsync(host_stats, p->stats_dev, sizeof(host_stats), cudaMemcpyDeviceToHost, p->d2h));
+  }
+  ok(cudaEventRecord(p->done, p->d2h));
+  ok(cudaStreamWaitEvent(caller, p->done, 0));
+  ok(cudaEventSynchronize(p->done));          // the result is host memory: hand it back complete
+  if (err != cudaSuccess) return cuda_fail(err, "streaming round trip");
+  if (stats != nullptr) {
+    stats[0] = static_cast<double>(host_stats[0]);
+    stats[1] = static_cast<double>(host_stats[1]);
+    stats[2] = static_cast<double>(host_stats[2]) / 65536.0;
+  }
+  return AC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- DLPack
 int ac_mdct_forward_dl(const ac_mdct_plan* plan, struct DLManagedTensor* x, struct DLManagedTensor* y, void* stream) {
   if (plan == nullptr) return fail(AC_ERR_INVALID, "plan is null");

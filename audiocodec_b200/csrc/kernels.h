@@ -85,6 +85,8 @@ cudaError_t pa_threshold(const PaDeviceTables& tb, const float* y, const float* 
 
 cudaError_t quantize(const float* y, const float* thr, int32_t* q, int64_t n, cudaStream_t stream);
 cudaError_t dequantize(const int32_t* q, const float* thr, float* y, int64_t n, cudaStream_t stream);
+// stats[0..2] += { n, non-zero integers, sum of log2(2|q|+1) in 16.16 fixed point }
+cudaError_t codec_stats(const int32_t* q, int64_t n, unsigned long long* stats, cudaStream_t stream);
 cudaError_t add_noise(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, cudaStream_t stream);
 
 }  // namespace ac

@@ -118,6 +118,22 @@ int ac_pa_add_noise_f32(const float* y, const float* thr, float* out, int64_t n,
 int ac_quantize_f32(const float* y, const float* thr, int32_t* q, int64_t n, void* stream);
 int ac_dequantize_f32(const int32_t* q, const float* thr, float* y, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------- host-buffer streaming */
+/* encode + decode of clips that live in HOST memory (the call a file / network front end makes; no reference
+ * symbol - the reference leaves data movement to TensorFlow).  The pipeline owns three streams and a ring of
+ * device workspaces for chunks of `chunk_clips` clips of [samples, channels]; x_host [B, S, C] flows
+ * H2D -> ac_mdct_forward -> ac_pa_encode -> ac_mdct_inverse_dequant -> D2H into xhat_host [B, S + 2N, C] with
+ * both PCIe directions and the kernels overlapped.  Pinned host memory gives asynchronous copies (pageable
+ * memory works, serialised).  ac_codec_roundtrip_host_f32 orders itself after the work already enqueued on
+ * `stream` and returns when xhat_host is complete.  stats (may be NULL) receives
+ * { coefficients, non-zero integers, sum log2(2|q|+1) } accumulated over the call, as doubles. */
+typedef struct ac_codec_pipeline ac_codec_pipeline;
+int ac_codec_pipeline_create(const ac_mdct_plan* mdct, const ac_pa_plan* pa, int64_t chunk_clips, int64_t samples,
+                             int channels, ac_codec_pipeline** out);
+int ac_codec_pipeline_destroy(ac_codec_pipeline* pipe);
+int ac_codec_roundtrip_host_f32(ac_codec_pipeline* pipe, const float* x_host, float* xhat_host, int64_t batches,
+                                float drown, float thr_scale, double* stats, void* stream);
+
 /* ------------------------------------------------------------------------------------------ DLPack */
 /* Same operations on DLManagedTensor* (what `tensor.__dlpack__()` / tf.experimental.dlpack.to_dlpack put
  * in the "dltensor" capsule).  Tensors are validated (kDLCUDA, float32 / int32, rank, compact strides,

@@ -191,3 +191,27 @@ def test_dlpack_entry_points(golden):
   assert torch.equal(ton, ton_ptr) and torch.equal(thr, thr_ptr)
   _capi.check(_capi.lib().ac_pa_threshold_dl(plan, _capi.dl_pointer(cy), None, 0.1, _capi.dl_pointer(ch), stream))
   np.testing.assert_allclose(thr.cpu().numpy(), thr_ptr.cpu().numpy(), rtol=1e-5)
+
+
+def test_host_streaming_round_trip_matches_device_path():
+  """AudioCodec.roundtrip_host (C pipeline: H2D, kernels, D2H over three streams) == encode + decode on the device."""
+  sr, n, c, b = 44100, 256, 2, 11
+  x = oracle.synthetic_audio(b, 256 * 50, c, sr)
+  codec = audiocodec_b200.AudioCodec(sr, filters_n=n)
+  xh = torch.from_numpy(x).pin_memory()
+  q, step = codec.encode(torch.from_numpy(x).cuda())
+  ref = codec.decode(q, step).cpu()
+  for chunk in (1, 3, 4, 16):
+    out, stats = codec.roundtrip_host(xh, chunk_clips=chunk, return_stats=True)
+    assert torch.equal(out, ref)
+    assert stats[0].item() == q.numel()
+    assert stats[1].item() == (q != 0).sum().item()
+    bits = torch.log2(2.0 * q.abs().double() + 1.0).sum().item()
+    assert abs(stats[2].item() - bits) <= 1e-4 * bits
+  out2 = codec.roundtrip_host(torch.from_numpy(x))             # pageable host memory also works
+  assert torch.equal(out2, ref)
+  with pytest.raises(TypeError):
+    codec.roundtrip_host(torch.from_numpy(x).cuda())
+  with pytest.raises(ValueError):
+    codec.roundtrip_host(torch.zeros(1, 100, 2))
+  assert tuple(codec.roundtrip_host(torch.zeros(0, 512, 2)).shape) == (0, 1024, 2)
