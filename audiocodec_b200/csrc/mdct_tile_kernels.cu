@@ -445,7 +445,7 @@ bool mdct_tile_forward_supported(int n, int channels) {
 }
 
 bool mdct_tile_inverse_supported(int n, int channels) {
-  return (channels == 1 || channels == 2) && (n == 64 || n == 128 || n == 256 || n == 512);
+  return (channels == 1 || channels == 2) && (n == 64 || n == 128 || n == 256 || n == 512 || n == 1024);
 }
 
 cudaError_t mdct_forward_tile(const MdctDeviceTables& tb, const float* x, float* y, int64_t batches, int64_t blocks_n,
@@ -476,6 +476,7 @@ cudaError_t mdct_inverse_tile(const MdctDeviceTables& tb, const float* y, const 
     case 128: AC_INV(Plan128, 128, 4);
     case 256: AC_INV(Plan256, 128, 3);
     case 512: AC_INV(Plan512, 128, 3);
+    case 1024: AC_INV(Plan1024, 256, 1);
     default: return cudaErrorInvalidConfiguration;
   }
 #undef AC_INV
