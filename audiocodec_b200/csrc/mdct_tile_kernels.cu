@@ -12,9 +12,9 @@
 //     post-twiddle writes its two outputs straight into the transposed positions;
 //   * a frame's shared-memory row is reused in place: input block -> FFT exchange scratch (XOR-swizzled
 //     instead of padded) -> output frame, so a tile needs (frames + 1) rows and several CTAs fit per SM;
-//   * the groups of a half-warp alternate the order of their two strided accesses ("variant"), which puts
-//     them on complementary bank classes: the stride-2 access pattern of the DCT-IV costs no conflicts;
-//   * the FFT passes of a group synchronise with __syncwarp (a group is at most one warp for N <= 1024).
+//   * the two quarter-warps of a half-warp make their two strided accesses in opposite order ("variant"), which
+//     puts them on complementary bank classes: the stride-2 access pattern of the DCT-IV costs no conflicts;
+//   * the FFT passes of a group synchronise with __syncwarp (groups of up to a warp) or a named barrier.
 //
 // tools/emulate_mdct_tile.py is a NumPy emulation of exactly this index arithmetic (development aid).
 #include "kernels.h"
@@ -27,12 +27,13 @@ namespace ac {
 
 namespace {
 
+// the T threads of group g meet: a warp-level sync when the group is (part of) one warp, else a named barrier
 template <int T>
-__device__ __forceinline__ void group_sync() {
+__device__ __forceinline__ void group_sync(int g) {
   if constexpr (T <= 32) {
     __syncwarp();
   } else {
-    __syncthreads();
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(T) : "memory");
   }
 }
 
@@ -108,7 +109,7 @@ __device__ __forceinline__ void pass_from_scratch(float2* v0, float2* v1, const 
 // On entry v0 / v1 hold the pass-0 inputs in Plan::in_index order and nobody reads `scratch` any more; on exit
 // they hold the spectra in Plan::out_index order and every read of `scratch` by this group has completed.
 template <typename Plan>
-__device__ __forceinline__ void fft2(float2* v0, float2* v1, float4* scratch, int t, const float2* __restrict__ roots) {
+__device__ __forceinline__ void fft2(float2* v0, float2* v1, float4* scratch, int t, int g, const float2* __restrict__ roots) {
   constexpr int E = Plan::E, T = Plan::T, R0 = Plan::R0, R1 = Plan::R1, R2 = Plan::R2;
 #pragma unroll
   for (int q = 0; q < E / R0; ++q) {
@@ -117,15 +118,15 @@ __device__ __forceinline__ void fft2(float2* v0, float2* v1, float4* scratch, in
   }
   if constexpr (R1 > 1) {
     pass_to_scratch<Plan, R0, 1>(v0, v1, scratch, t);
-    group_sync<T>();
+    group_sync<T>(g);
     pass_from_scratch<Plan, R1, R0>(v0, v1, scratch, t, roots);
     if constexpr (R2 > 1) {
-      group_sync<T>();
+      group_sync<T>(g);
       pass_to_scratch<Plan, R1, R0>(v0, v1, scratch, t);
-      group_sync<T>();
+      group_sync<T>(g);
       pass_from_scratch<Plan, R2, R0 * R1>(v0, v1, scratch, t, roots);
     }
-    group_sync<T>();
+    group_sync<T>(g);
   }
 }
 
@@ -167,7 +168,7 @@ mdct_forward_tile_kernel(MdctDeviceTables tb, const float* __restrict__ x, float
   float* bufs = reinterpret_cast<float*>(smem_raw);                   // [2][FP + 1][ROW]: row r = block f0 - 1 + r
   uint64_t* mbar = reinterpret_cast<uint64_t*>(bufs + 2 * BUF);       // [2]
 
-  const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = g & 1;
+  const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = (tid >> 3) & 1;
   const int frames = blocks_n + 1;
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
@@ -237,7 +238,7 @@ mdct_forward_tile_kernel(MdctDeviceTables tb, const float* __restrict__ x, float
       issue_load(tile + gridDim.x, slot ^ 1);
     }
 
-    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(cur), t, tb.roots);
+    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(cur), t, g, tb.roots);
     post_store<Plan, C, ROW>(v0, v1, cur, t, variant, tb.post_fwd);
     fence_async_smem();
     __syncthreads();
@@ -265,7 +266,7 @@ mdct_inverse_tile_kernel(MdctDeviceTables tb, const float* __restrict__ y, const
   float* bbuf = abuf + FP * ROW;                         // [FP][ROW]: quantised integers -> output blocks
   uint64_t* mbar = reinterpret_cast<uint64_t*>(bbuf + FP * ROW);
 
-  const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = g & 1;
+  const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = (tid >> 3) & 1;
   float* arow = abuf + g * (2 / C) * ROW;
   const int32_t* qrow = reinterpret_cast<const int32_t*>(bbuf) + g * (2 / C) * ROW;
   if (tid == 0) {
@@ -336,9 +337,9 @@ mdct_inverse_tile_kernel(MdctDeviceTables tb, const float* __restrict__ y, const
       v0[s] = make_float2(fmaf(l2.x, k4.y, l1.x * k4.x), fmaf(l2.x, k4.w, l1.x * k4.z));
       v1[s] = make_float2(fmaf(l2.y, k4.y, l1.y * k4.x), fmaf(l2.y, k4.w, l1.y * k4.z));
     }
-    group_sync<T>();                           // the group's rows have been read: they become its scratch
+    group_sync<T>(g);                           // the group's rows have been read: they become its scratch
 
-    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(arow), t, tb.roots);
+    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(arow), t, g, tb.roots);
     post_store<Plan, C, ROW>(v0, v1, arow, t, variant, tb.post_inv);
     __syncthreads();
 
@@ -423,7 +424,7 @@ using Plan64 = FftPlan<32, 8, 8, 4, 1>;
 using Plan128 = FftPlan<64, 8, 8, 8, 1>;
 using Plan256 = FftPlan<128, 16, 16, 8, 1>;
 using Plan512 = FftPlan<256, 16, 16, 16, 1>;
-using Plan1024 = FftPlan<512, 16, 8, 8, 8>;
+using Plan1024 = FftPlan<512, 8, 8, 8, 8>;      // 64 threads per transform pair: named barriers, 16 warps per SM
 
 }  // namespace
 
@@ -459,7 +460,7 @@ cudaError_t mdct_forward_tile(const MdctDeviceTables& tb, const float* x, float*
     case 128: AC_FWD(Plan128, 128, 4);
     case 256: AC_FWD(Plan256, 128, 3);
     case 512: AC_FWD(Plan512, 128, 3);
-    case 1024: AC_FWD(Plan1024, 256, 1);
+    case 1024: AC_FWD(Plan1024, 512, 1);
     default: return cudaErrorInvalidConfiguration;
   }
 #undef AC_FWD
@@ -476,7 +477,7 @@ cudaError_t mdct_inverse_tile(const MdctDeviceTables& tb, const float* y, const 
     case 128: AC_INV(Plan128, 128, 4);
     case 256: AC_INV(Plan256, 128, 3);
     case 512: AC_INV(Plan512, 128, 3);
-    case 1024: AC_INV(Plan1024, 256, 1);
+    case 1024: AC_INV(Plan1024, 512, 1);
     default: return cudaErrorInvalidConfiguration;
   }
 #undef AC_INV
