@@ -215,3 +215,14 @@ def test_host_streaming_round_trip_matches_device_path():
   with pytest.raises(ValueError):
     codec.roundtrip_host(torch.zeros(1, 100, 2))
   assert tuple(codec.roundtrip_host(torch.zeros(0, 512, 2)).shape) == (0, 1024, 2)
+
+
+def test_quantizer_odd_sizes_take_the_scalar_kernel():
+  rng = np.random.default_rng(3)
+  pa = audiocodec_b200.PsychoacousticModel(44100, 8)
+  for shape in ((1, 1, 7, 1), (2, 3, 5, 3), (1, 2, 8, 2)):
+    y = rng.standard_normal(shape).astype(np.float32)
+    thr = (rng.random(shape).astype(np.float32) * 0.1 + 1e-3)
+    q = pa.quantize(cuda(y), cuda(thr))
+    assert np.array_equal(q.cpu().numpy(), oracle.quantize(y, thr))
+    assert np.array_equal(pa.dequantize(q, cuda(thr)).cpu().numpy(), oracle.dequantize(q.cpu().numpy(), thr))
