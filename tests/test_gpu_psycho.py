@@ -71,7 +71,11 @@ def test_against_reference_fixture(golden, name, sr, n, nb, alpha):
 
 @pytest.mark.parametrize("sr,n,nb,alpha,b,m,c", [(44100, 256, 64, 0.6, 3, 17, 2), (48000, 1024, 64, 0.6, 2, 9, 2),
                                                    (22050, 512, 48, 0.5, 2, 5, 1), (44100, 2048, 64, 0.6, 1, 3, 2),
-                                                   (8000, 32, 16, 1.0, 2, 6, 3), (44100, 100, 40, 0.6, 2, 4, 1)])
+                                                   (8000, 32, 16, 1.0, 2, 6, 3), (44100, 100, 40, 0.6, 2, 4, 1),
+                                                   # tile kernel: mono / four channels, ragged last tile, odd N
+                                                   (44100, 256, 64, 0.6, 3, 23, 1), (44100, 256, 64, 0.6, 2, 5, 4),
+                                                   (48000, 1024, 64, 0.6, 1, 7, 4), (44100, 320, 64, 0.6, 2, 9, 2),
+                                                   (44100, 4096, 64, 0.6, 1, 2, 1)])
 def test_against_oracle_random_spectra(sr, n, nb, alpha, b, m, c):
   rng = np.random.default_rng(n + nb)
   # spectra with a large dynamic range, including exact zeros
@@ -134,8 +138,9 @@ def test_end_to_end_quantised_integers(sr, n, c):
   assert abs(err - err_ref) <= 1e-3 * err_ref
 
 
-def test_encode_matches_unfused_chain():
-  x = cuda(oracle.synthetic_audio(3, 256 * 30, 2, 44100))
+@pytest.mark.parametrize("channels", [1, 2, 4, 3])
+def test_encode_matches_unfused_chain(channels):
+  x = cuda(oracle.synthetic_audio(3, 256 * 30, channels, 44100))
   codec = audiocodec_b200.AudioCodec(44100, filters_n=256)
   y = codec.mdct.transform(x)
   pa = codec.psychoacoustic
