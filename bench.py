@@ -92,12 +92,23 @@ def cpu_port_throughput(name, budget_s, steps=1, warmup=0, threads=None):
   def one_step():
     list(pool.map(lambda x: _oracle_chain(x, mdct, pa, oracle), xs))
 
-  for _ in range(warmup):
-    one_step()
-  t0 = time.perf_counter()
-  for _ in range(steps):
-    one_step()
-  elapsed = time.perf_counter() - t0
+  # one clip per worker thread, BLAS kept single-threaded inside each: without the limit every worker's matmul
+  # spawns a full BLAS team and the oversubscription costs the port a factor of three
+  try:
+    from threadpoolctl import threadpool_limits
+    limit = threadpool_limits(limits=1)
+  except ImportError:
+    limit = None
+  try:
+    for _ in range(warmup):
+      one_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+      one_step()
+    elapsed = time.perf_counter() - t0
+  finally:
+    if limit is not None:
+      limit.restore_original_limits()
   pool.shutdown()
   audio_s = clips * s / sr * steps
   info = {"cores": min(threads, clips), "clips_per_step": clips, "steps": steps, "seconds": elapsed,
