@@ -495,15 +495,9 @@ int ac_dequantize_f32(const int32_t* q, const float* thr, float* y, int64_t n, v
 }
 
 // --------------------------------------------------------------------------------- host-buffer streaming
-namespace {
-constexpr int kPipeSlots = 3;
-struct PipeSlot {
-  float *x = nullptr, *y = nullptr, *step = nullptr, *xhat = nullptr;
-  int32_t* q = nullptr;
-  cudaEvent_t x_ready = nullptr, x_free = nullptr, out_ready = nullptr, out_free = nullptr;
-};
-}  // namespace
-
+// Device memory is plentiful (180 GB): the whole batch of x and x_hat is staged on the device, so the H2D stream
+// never waits for the kernels and the D2H stream only trails them; amplitudes, steps and integers need one
+// chunk-sized set because the kernels of all chunks run in order on one stream.
 struct ac_codec_pipeline {
   const ac_mdct_plan* mdct = nullptr;
   const ac_pa_plan* pa = nullptr;
@@ -511,24 +505,24 @@ struct ac_codec_pipeline {
   int channels = 0, device = 0;
   cudaStream_t h2d = nullptr, run = nullptr, d2h = nullptr;
   cudaEvent_t entry = nullptr, done = nullptr;
-  PipeSlot slots[kPipeSlots];
+  float *y = nullptr, *step = nullptr;        // one chunk
+  int32_t* q = nullptr;
+  float *x_all = nullptr, *xhat_all = nullptr;   // capacity_clips clips, grown on demand
+  int64_t capacity_clips = 0;
+  std::vector<cudaEvent_t> x_ready, out_ready;   // one pair per chunk of the largest batch seen
   unsigned long long* stats_dev = nullptr;   // [3] coefficients, non-zeros, fixed-point sum of log2(2|q|+1)
 };
 
 int ac_codec_pipeline_destroy(ac_codec_pipeline* p) {
   if (p == nullptr) return AC_OK;
-  for (PipeSlot& s : p->slots) {
-    cudaFree(s.x);
-    cudaFree(s.y);
-    cudaFree(s.step);
-    cudaFree(s.xhat);
-    cudaFree(s.q);
-    if (s.x_ready) cudaEventDestroy(s.x_ready);
-    if (s.x_free) cudaEventDestroy(s.x_free);
-    if (s.out_ready) cudaEventDestroy(s.out_ready);
-    if (s.out_free) cudaEventDestroy(s.out_free);
-  }
+  cudaFree(p->y);
+  cudaFree(p->step);
+  cudaFree(p->q);
+  cudaFree(p->x_all);
+  cudaFree(p->xhat_all);
   cudaFree(p->stats_dev);
+  for (cudaEvent_t e : p->x_ready) cudaEventDestroy(e);
+  for (cudaEvent_t e : p->out_ready) cudaEventDestroy(e);
   if (p->entry) cudaEventDestroy(p->entry);
   if (p->done) cudaEventDestroy(p->done);
   if (p->h2d) cudaStreamDestroy(p->h2d);
@@ -556,9 +550,7 @@ int ac_codec_pipeline_create(const ac_mdct_plan* mdct, const ac_pa_plan* pa, int
   p->samples = samples;
   p->channels = channels;
   const size_t frames = static_cast<size_t>(samples / n + 1);
-  const size_t in_elems = static_cast<size_t>(chunk_clips) * samples * channels;
-  const size_t amp_elems = static_cast<size_t>(chunk_clips) * frames * n * channels;
-  const size_t out_elems = static_cast<size_t>(chunk_clips) * (frames + 1) * n * channels;
+  const size_t amp_elems = std::max<size_t>(static_cast<size_t>(chunk_clips) * frames * n * channels, 4);
   cudaError_t err = cudaGetDevice(&p->device);
   auto ok = [&](cudaError_t e) {
     if (err == cudaSuccess) err = e;
@@ -570,17 +562,9 @@ int ac_codec_pipeline_create(const ac_mdct_plan* mdct, const ac_pa_plan* pa, int
   ok(cudaEventCreateWithFlags(&p->entry, cudaEventDisableTiming));
   ok(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
   ok(cudaMalloc(reinterpret_cast<void**>(&p->stats_dev), 3 * sizeof(unsigned long long)));
-  for (PipeSlot& s : p->slots) {
-    ok(cudaMalloc(reinterpret_cast<void**>(&s.x), std::max<size_t>(in_elems, 4) * sizeof(float)));
-    ok(cudaMalloc(reinterpret_cast<void**>(&s.y), amp_elems * sizeof(float)));
-    ok(cudaMalloc(reinterpret_cast<void**>(&s.step), amp_elems * sizeof(float)));
-    ok(cudaMalloc(reinterpret_cast<void**>(&s.q), amp_elems * sizeof(int32_t)));
-    ok(cudaMalloc(reinterpret_cast<void**>(&s.xhat), out_elems * sizeof(float)));
-    ok(cudaEventCreateWithFlags(&s.x_ready, cudaEventDisableTiming));
-    ok(cudaEventCreateWithFlags(&s.x_free, cudaEventDisableTiming));
-    ok(cudaEventCreateWithFlags(&s.out_ready, cudaEventDisableTiming));
-    ok(cudaEventCreateWithFlags(&s.out_free, cudaEventDisableTiming));
-  }
+  ok(cudaMalloc(reinterpret_cast<void**>(&p->y), amp_elems * sizeof(float)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&p->step), amp_elems * sizeof(float)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&p->q), amp_elems * sizeof(int32_t)));
   if (err != cudaSuccess) {
     ac_codec_pipeline_destroy(p);
     return cuda_fail(err, "creating the streaming pipeline");
@@ -603,36 +587,56 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
     if (err == cudaSuccess) err = e;
     return err == cudaSuccess;
   };
+  // staging for the whole batch and one event pair per chunk (grown on demand, kept for the next call)
+  if (batches > p->capacity_clips) {
+    cudaFree(p->x_all);
+    cudaFree(p->xhat_all);
+    p->x_all = p->xhat_all = nullptr;
+    p->capacity_clips = 0;
+    ok(cudaMalloc(reinterpret_cast<void**>(&p->x_all), std::max<size_t>(batches * in_clip, 4) * sizeof(float)));
+    ok(cudaMalloc(reinterpret_cast<void**>(&p->xhat_all), batches * out_clip * sizeof(float)));
+    if (err != cudaSuccess) return cuda_fail(err, "allocating the device staging of the batch");
+    p->capacity_clips = batches;
+  }
+  const size_t n_chunks = static_cast<size_t>((batches + p->chunk_clips - 1) / p->chunk_clips);
+  while (p->x_ready.size() < n_chunks && err == cudaSuccess) {
+    cudaEvent_t a = nullptr, b = nullptr;
+    ok(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    if (err == cudaSuccess) {
+      p->x_ready.push_back(a);
+      p->out_ready.push_back(b);
+    }
+  }
   cudaStream_t caller = static_cast<cudaStream_t>(stream);
   ok(cudaEventRecord(p->entry, caller));
   ok(cudaStreamWaitEvent(p->h2d, p->entry, 0));
   ok(cudaStreamWaitEvent(p->run, p->entry, 0));
   ok(cudaStreamWaitEvent(p->d2h, p->entry, 0));
   if (stats != nullptr) ok(cudaMemsetAsync(p->stats_dev, 0, 3 * sizeof(unsigned long long), p->run));
-  int k = 0;
+  // all the H2D copies first: nothing on that stream depends on the kernels
+  size_t k = 0;
   for (int64_t i = 0; i < batches && err == cudaSuccess; i += p->chunk_clips, ++k) {
     const int64_t cb = std::min(p->chunk_clips, batches - i);
-    PipeSlot& sl = p->slots[k % kPipeSlots];
-    if (k >= kPipeSlots) ok(cudaStreamWaitEvent(p->h2d, sl.x_free, 0));
-    if (in_clip > 0) ok(cudaMemcpyAsync(sl.x, x_host + i * in_clip, cb * in_clip * sizeof(float), cudaMemcpyHostToDevice, p->h2d));
-    ok(cudaEventRecord(sl.x_ready, p->h2d));
-    ok(cudaStreamWaitEvent(p->run, sl.x_ready, 0));
-    ok(ac::mdct_forward(p->mdct->tb, sl.x, sl.y, cb, blocks, c, p->run));
-    ok(cudaEventRecord(sl.x_free, p->run));
-    ok(ac::pa_threshold(p->pa->tb, sl.y, nullptr, drown, thr_scale, sl.step, sl.q, cb * frames, c, p->run));
-    if (stats != nullptr) ok(ac::codec_stats(sl.q, cb * frames * n * c, p->stats_dev, p->run));
-    if (k >= kPipeSlots) ok(cudaStreamWaitEvent(p->run, sl.out_free, 0));
-    ok(ac::mdct_inverse(p->mdct->tb, nullptr, sl.q, sl.step, sl.xhat, cb, frames, c, p->run));
-    ok(cudaEventRecord(sl.out_ready, p->run));
-    ok(cudaStreamWaitEvent(p->d2h, sl.out_ready, 0));
-    ok(cudaMemcpyAsync(xhat_host + i * out_clip, sl.xhat, cb * out_clip * sizeof(float), cudaMemcpyDeviceToHost, p->d2h));
-    ok(cudaEventRecord(sl.out_free, p->d2h));
+    if (in_clip > 0)
+      ok(cudaMemcpyAsync(p->x_all + i * in_clip, x_host + i * in_clip, cb * in_clip * sizeof(float), cudaMemcpyHostToDevice, p->h2d));
+    ok(cudaEventRecord(p->x_ready[k], p->h2d));
+  }
+  k = 0;
+  for (int64_t i = 0; i < batches && err == cudaSuccess; i += p->chunk_clips, ++k) {
+    const int64_t cb = std::min(p->chunk_clips, batches - i);
+    float* xh = p->xhat_all + i * out_clip;
+    ok(cudaStreamWaitEvent(p->run, p->x_ready[k], 0));
+    ok(ac::mdct_forward(p->mdct->tb, p->x_all + i * in_clip, p->y, cb, blocks, c, p->run));
+    ok(ac::pa_threshold(p->pa->tb, p->y, nullptr, drown, thr_scale, p->step, p->q, cb * frames, c, p->run));
+    if (stats != nullptr) ok(ac::codec_stats(p->q, cb * frames * n * c, p->stats_dev, p->run));
+    ok(ac::mdct_inverse(p->mdct->tb, nullptr, p->q, p->step, xh, cb, frames, c, p->run));
+    ok(cudaEventRecord(p->out_ready[k], p->run));
+    ok(cudaStreamWaitEvent(p->d2h, p->out_ready[k], 0));
+    ok(cudaMemcpyAsync(xhat_host + i * out_clip, xh, cb * out_clip * sizeof(float), cudaMemcpyDeviceToHost, p->d2h));
   }
   unsigned long long host_stats[3] = {0, 0, 0};
-  if (stats != nullptr) {
-    ok(cudaStreamWaitEvent(p->d2h, p->slots[(k + kPipeSlots - 1) % kPipeSlots].out_ready, 0));
-    ok(cudaMemcpyAsync(host_stats, p->stats_dev, sizeof(host_stats), cudaMemcpyDeviceToHost, p->d2h));
-  }
+  if (stats != nullptr) ok(cudaMemcpyAsync(host_stats, p->stats_dev, sizeof(host_stats), cudaMemcpyDeviceToHost, p->d2h));
   ok(cudaEventRecord(p->done, p->d2h));
   ok(cudaStreamWaitEvent(caller, p->done, 0));
   ok(cudaEventSynchronize(p->done));          // the result is host memory: hand it back complete

@@ -120,8 +120,9 @@ int ac_dequantize_f32(const int32_t* q, const float* thr, float* y, int64_t n, v
 
 /* ------------------------------------------------------------------------- host-buffer streaming */
 /* encode + decode of clips that live in HOST memory (the call a file / network front end makes; no reference
- * symbol - the reference leaves data movement to TensorFlow).  The pipeline owns three streams and a ring of
- * device workspaces for chunks of `chunk_clips` clips of [samples, channels]; x_host [B, S, C] flows
+ * symbol - the reference leaves data movement to TensorFlow).  The pipeline owns three streams, device staging
+ * for the whole batch of x and x_hat (grown on demand) and one chunk of amplitudes / steps / integers;
+ * x_host [B, S, C] flows in chunks of `chunk_clips` clips through
  * H2D -> ac_mdct_forward -> ac_pa_encode -> ac_mdct_inverse_dequant -> D2H into xhat_host [B, S + 2N, C] with
  * both PCIe directions and the kernels overlapped.  Pinned host memory gives asynchronous copies (pageable
  * memory works, serialised).  ac_codec_roundtrip_host_f32 orders itself after the work already enqueued on
