@@ -224,10 +224,11 @@ int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_m
     } else {
       for (int i = 0; i < 4; ++i) re[i] = im[i] = 0.0;
     }
-    pre_fwd[(0 * h + m) * 2] = make_float4((float)re[0], (float)re[1], (float)re[2], (float)re[3]);
-    pre_fwd[(0 * h + m) * 2 + 1] = make_float4((float)im[0], (float)im[1], (float)im[2], (float)im[3]);
-    pre_fwd[(1 * h + m) * 2] = make_float4((float)re[1], (float)re[0], (float)re[3], (float)re[2]);
-    pre_fwd[(1 * h + m) * 2 + 1] = make_float4((float)im[1], (float)im[0], (float)im[3], (float)im[2]);
+    // layout [variant][Re / Im][n]: the eight lanes of a quarter-warp read one contiguous 128-byte line
+    pre_fwd[(0 * 2 + 0) * h + m] = make_float4((float)re[0], (float)re[1], (float)re[2], (float)re[3]);
+    pre_fwd[(0 * 2 + 1) * h + m] = make_float4((float)im[0], (float)im[1], (float)im[2], (float)im[3]);
+    pre_fwd[(1 * 2 + 0) * h + m] = make_float4((float)re[1], (float)re[0], (float)re[3], (float)re[2]);
+    pre_fwd[(1 * 2 + 1) * h + m] = make_float4((float)im[1], (float)im[0], (float)im[3], (float)im[2]);
     // first store S1 = vx c0 + vy c1, second S2 = vx c2 + vy c3; variant 0: S1 = Re D -> [2k], S2 = -Im D -> [N-1-2k]
     const double fx = c * scale_fwd, fy = s * scale_fwd, ix = c * scale_inv, iy = s * scale_inv;
     post_fwd[0 * h + m] = make_float4((float)fx, (float)-fy, (float)-fy, (float)-fx);

@@ -20,7 +20,7 @@ struct MdctDeviceTables {
   const float2* roots = nullptr;     // [N/2]  exp(-2 pi i j / (N/2))
   const float* cos_table = nullptr;  // [8N]   cos(pi m / (4N)), generic-N path only
   // tile kernels (mdct_tile_kernels.cu), [variant][n]: host-merged coefficients, see capi.cu
-  const float4* pre_fwd = nullptr;   // [2][N/2][2]  fold x pre-twiddle: Re / Im as dot products of the four samples
+  const float4* pre_fwd = nullptr;   // [2][2][N/2]  fold x pre-twiddle: Re / Im as dot products of the four samples
   const float4* post_fwd = nullptr;  // [2][N/2]     post-twiddle x 1 / (N sqrt 2), as the two stored outputs
   const float4* pre_inv = nullptr;   // [2][N/2]     pre-twiddle of the inverse
   const float4* post_inv = nullptr;  // [2][N/2]     post-twiddle x 2 sqrt 2

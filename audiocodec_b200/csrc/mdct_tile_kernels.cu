@@ -225,8 +225,8 @@ mdct_forward_tile_kernel(MdctDeviceTables tb, const float* __restrict__ x, float
       const int a2 = (N - 1) - a1;
       const float2 l0 = ld2<C, ROW>(prev, a1), l1 = ld2<C, ROW>(prev, a2);
       const float2 l2 = ld2<C, ROW>(cur, a1), l3 = ld2<C, ROW>(cur, a2);
-      const float4 kr = __ldg(&tb.pre_fwd[(variant * M + n) * 2]);
-      const float4 ki = __ldg(&tb.pre_fwd[(variant * M + n) * 2 + 1]);
+      const float4 kr = __ldg(&tb.pre_fwd[(variant * 2) * M + n]);
+      const float4 ki = __ldg(&tb.pre_fwd[(variant * 2 + 1) * M + n]);
       v0[s].x = fmaf(l3.x, kr.w, fmaf(l2.x, kr.z, fmaf(l1.x, kr.y, l0.x * kr.x)));
       v0[s].y = fmaf(l3.x, ki.w, fmaf(l2.x, ki.z, fmaf(l1.x, ki.y, l0.x * ki.x)));
       v1[s].x = fmaf(l3.y, kr.w, fmaf(l2.y, kr.z, fmaf(l1.y, kr.y, l0.y * kr.x)));
