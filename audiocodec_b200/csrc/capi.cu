@@ -239,6 +239,23 @@ int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_m
     pre_inv[0 * h + m] = make_float4((float)c, (float)-s, (float)s, (float)c);
     pre_inv[1 * h + m] = make_float4((float)-s, (float)c, (float)c, (float)s);
   }
+  std::vector<float2> tw_pass1, tw_pass2;
+  {
+    int r0 = 1, r1 = 1, r2 = 1;
+    if (ac::tile_fft_radices(n, &r0, &r1, &r2)) {
+      auto build = [&](int radix, int ns, std::vector<float2>& out) {
+        const int per = h / radix;                    // butterflies of the pass
+        out.resize(static_cast<size_t>(radix - 1) * per);
+        for (int r = 1; r < radix; ++r)
+          for (int j = 0; j < per; ++j) {
+            const double ang = -2.0 * pi * r * (j % ns) / (static_cast<double>(ns) * radix);
+            out[static_cast<size_t>(r - 1) * per + j] = make_float2((float)std::cos(ang), (float)std::sin(ang));
+          }
+      };
+      if (r1 > 1) build(r1, r0, tw_pass1);
+      if (r2 > 1) build(r2, r0 * r1, tw_pass2);
+    }
+  }
   std::vector<float> cos_table;
   if (!fast) {
     cos_table.resize(static_cast<size_t>(8) * n);
@@ -257,7 +274,9 @@ int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_m
       (err = upload(pre_fwd, &plan->tb.pre_fwd, plan->owned)) != cudaSuccess ||
       (err = upload(post_fwd, &plan->tb.post_fwd, plan->owned)) != cudaSuccess ||
       (err = upload(pre_inv, &plan->tb.pre_inv, plan->owned)) != cudaSuccess ||
-      (err = upload(post_inv, &plan->tb.post_inv, plan->owned)) != cudaSuccess) {
+      (err = upload(post_inv, &plan->tb.post_inv, plan->owned)) != cudaSuccess ||
+      (err = upload(tw_pass1, &plan->tb.tw_pass1, plan->owned)) != cudaSuccess ||
+      (err = upload(tw_pass2, &plan->tb.tw_pass2, plan->owned)) != cudaSuccess) {
     free_all(plan->owned);
     delete plan;
     return cuda_fail(err, "uploading MDCT tables");

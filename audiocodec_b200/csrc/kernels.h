@@ -24,7 +24,23 @@ struct MdctDeviceTables {
   const float4* post_fwd = nullptr;  // [2][N/2]     post-twiddle x 1 / (N sqrt 2), as the two stored outputs
   const float4* pre_inv = nullptr;   // [2][N/2]     pre-twiddle of the inverse
   const float4* post_inv = nullptr;  // [2][N/2]     post-twiddle x 2 sqrt 2
+  // inter-pass twiddles of the tile FFT, one contiguous row per butterfly input: tw_pass1[(r - 1) * (M / R1) + j] =
+  // exp(-2 pi i r (j mod R0) / (R0 R1)), tw_pass2 likewise for the third pass (radices from tile_fft_radices)
+  const float2* tw_pass1 = nullptr;
+  const float2* tw_pass2 = nullptr;
 };
+
+// radices of the tile kernels' FFT plan for filters_n = n (mdct_tile_kernels.cu); false when n has no tile plan
+inline bool tile_fft_radices(int n, int* r0, int* r1, int* r2) {
+  switch (n) {
+    case 64: *r0 = 8; *r1 = 4; *r2 = 1; return true;
+    case 128: *r0 = 8; *r1 = 8; *r2 = 1; return true;
+    case 256: *r0 = 16; *r1 = 8; *r2 = 1; return true;
+    case 512: *r0 = 16; *r1 = 16; *r2 = 1; return true;
+    case 1024: *r0 = 8; *r1 = 8; *r2 = 8; return true;
+    default: return false;
+  }
+}
 
 // Device-resident psychoacoustic tables (psychoacoustic.py:52-69, sparse forms from tables.h).
 struct PaDeviceTables {

@@ -79,7 +79,7 @@ __device__ __forceinline__ void pass_to_scratch(const float2* v0, const float2* 
 
 template <typename Plan, int R, int NS>
 __device__ __forceinline__ void pass_from_scratch(float2* v0, float2* v1, const float4* scratch, int t,
-                                                  const float2* __restrict__ roots) {
+                                                  const float2* __restrict__ tw) {
   constexpr int M = Plan::M, E = Plan::E, T = Plan::T;
 #pragma unroll
   for (int q = 0; q < E / R; ++q) {
@@ -94,10 +94,9 @@ __device__ __forceinline__ void pass_from_scratch(float2* v0, float2* v1, const 
 #pragma unroll
   for (int q = 0; q < E / R; ++q) {
     const int j = t + T * q;
-    const int k = j % NS;
 #pragma unroll
     for (int r = 1; r < R; ++r) {
-      const float2 w = __ldg(&roots[r * k * (M / (NS * R))]);
+      const float2 w = __ldg(&tw[(r - 1) * (M / R) + j]);      // exp(-2 pi i r (j mod NS) / (NS R)), contiguous in j
       v0[q * R + r] = cmul(v0[q * R + r], w);
       v1[q * R + r] = cmul(v1[q * R + r], w);
     }
@@ -109,7 +108,8 @@ __device__ __forceinline__ void pass_from_scratch(float2* v0, float2* v1, const 
 // On entry v0 / v1 hold the pass-0 inputs in Plan::in_index order and nobody reads `scratch` any more; on exit
 // they hold the spectra in Plan::out_index order and every read of `scratch` by this group has completed.
 template <typename Plan>
-__device__ __forceinline__ void fft2(float2* v0, float2* v1, float4* scratch, int t, int g, const float2* __restrict__ roots) {
+__device__ __forceinline__ void fft2(float2* v0, float2* v1, float4* scratch, int t, int g, const float2* __restrict__ tw1,
+                                     const float2* __restrict__ tw2) {
   constexpr int E = Plan::E, T = Plan::T, R0 = Plan::R0, R1 = Plan::R1, R2 = Plan::R2;
 #pragma unroll
   for (int q = 0; q < E / R0; ++q) {
@@ -119,12 +119,12 @@ __device__ __forceinline__ void fft2(float2* v0, float2* v1, float4* scratch, in
   if constexpr (R1 > 1) {
     pass_to_scratch<Plan, R0, 1>(v0, v1, scratch, t);
     group_sync<T>(g);
-    pass_from_scratch<Plan, R1, R0>(v0, v1, scratch, t, roots);
+    pass_from_scratch<Plan, R1, R0>(v0, v1, scratch, t, tw1);
     if constexpr (R2 > 1) {
       group_sync<T>(g);
       pass_to_scratch<Plan, R1, R0>(v0, v1, scratch, t);
       group_sync<T>(g);
-      pass_from_scratch<Plan, R2, R0 * R1>(v0, v1, scratch, t, roots);
+      pass_from_scratch<Plan, R2, R0 * R1>(v0, v1, scratch, t, tw2);
     }
     group_sync<T>(g);
   }
@@ -238,7 +238,7 @@ mdct_forward_tile_kernel(MdctDeviceTables tb, const float* __restrict__ x, float
       issue_load(tile + gridDim.x, slot ^ 1);
     }
 
-    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(cur), t, g, tb.roots);
+    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(cur), t, g, tb.tw_pass1, tb.tw_pass2);
     post_store<Plan, C, ROW>(v0, v1, cur, t, variant, tb.post_fwd);
     fence_async_smem();
     __syncthreads();
@@ -339,7 +339,7 @@ mdct_inverse_tile_kernel(MdctDeviceTables tb, const float* __restrict__ y, const
     }
     group_sync<T>(g);                           // the group's rows have been read: they become its scratch
 
-    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(arow), t, g, tb.roots);
+    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(arow), t, g, tb.tw_pass1, tb.tw_pass2);
     post_store<Plan, C, ROW>(v0, v1, arow, t, variant, tb.post_inv);
     __syncthreads();
 
