@@ -78,6 +78,10 @@ CASES = [  # n, window, B, blocks, C
   (2048, 'vorbis', 1, 11, 2), (4096, 'vorbis', 2, 5, 1), (4096, 'vorbis', 1, 3, 2),
   (12, 'ones', 2, 5, 3), (48, 'vorbis', 2, 9, 2), (100, 'sine', 1, 6, 1), (6, 'vorbis', 2, 4, 1),
   (256, 'vorbis', 2, 1, 2), (256, 'vorbis', 2, 0, 2), (64, 'vorbis', 1, 3, 5), (1024, 'vorbis', 1, 2, 12),
+  # tile kernels: rectangular window, tile-edge block counts (16 frames per stereo tile, 32 per mono tile), N = 512 mono
+  (256, 'ones', 2, 9, 2), (256, 'vorbis', 1, 15, 2), (256, 'vorbis', 1, 16, 2), (256, 'vorbis', 1, 17, 2),
+  (256, 'vorbis', 1, 31, 1), (256, 'vorbis', 1, 32, 1), (512, 'sine', 2, 23, 1), (128, 'vorbis', 3, 50, 2),
+  (1024, 'vorbis', 1, 16, 2), (1024, 'vorbis', 2, 7, 1),
 ]
 
 
@@ -215,6 +219,44 @@ def test_foreign_dlpack_tensor_is_adopted():
   x = torch.rand(1, 512, 1, device="cuda") - 0.5
   mdct = audiocodec_b200.MDCTransformer(256)
   assert torch.equal(mdct.transform(Foreign(x)), mdct.transform(x))
+
+
+def test_float32_precompute_on_the_tile_path():
+  rng = np.random.default_rng(17)
+  x = rng.uniform(-1, 1, (2, 256 * 20, 2)).astype(np.float32)
+  ref = oracle.MDCTransformer(256, compute_dtype=np.float64, precompute_dtype=np.float32)
+  mdct = audiocodec_b200.MDCTransformer(256, precompute_dtype='float32')
+  y = mdct.transform(cuda(x))
+  y_ref = ref.transform(x.astype(np.float64))
+  # float32 window chains differ by an ulp between sin() implementations and the consistency rule amplifies it
+  # (see test_mdct_float32_precompute_variant): a looser, still tight, bound
+  assert np.max(np.abs(y.cpu().numpy() - y_ref)) <= 5e-6
+  back = mdct.inverse_transform(y).cpu().numpy()
+  assert np.max(np.abs(back[:, 256:-256] - x)) < 2e-5
+
+
+def test_legacy_path_matches_tile_path():
+  """The any-channel-count kernels (AC_MDCT_LEGACY=1 in a fresh process) and the tile kernels agree to fp32 rounding."""
+  import os, subprocess, sys, tempfile
+  rng = np.random.default_rng(23)
+  x = rng.uniform(-1, 1, (3, 256 * 37, 2)).astype(np.float32)
+  mdct = audiocodec_b200.MDCTransformer(256)
+  y = mdct.transform(cuda(x)).cpu().numpy()
+  with tempfile.TemporaryDirectory() as tmp:
+    np.save(os.path.join(tmp, "x.npy"), x)
+    code = ("import numpy as np, torch, audiocodec_b200, sys\n"
+            "x = torch.from_numpy(np.load(sys.argv[1] + '/x.npy')).cuda()\n"
+            "m = audiocodec_b200.MDCTransformer(256)\n"
+            "y = m.transform(x)\n"
+            "np.save(sys.argv[1] + '/y.npy', y.cpu().numpy()); np.save(sys.argv[1] + '/b.npy', m.inverse_transform(y).cpu().numpy())\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, AC_MDCT_LEGACY="1", PYTHONPATH=root)
+    proc = subprocess.run([sys.executable, "-c", code, tmp], env=env, capture_output=True, text=True, timeout=300)
+    assert proc.returncode == 0, proc.stderr[-1500:]
+    y_legacy, back_legacy = np.load(os.path.join(tmp, "y.npy")), np.load(os.path.join(tmp, "b.npy"))
+  assert np.max(np.abs(y - y_legacy)) < 2e-7
+  back = mdct.inverse_transform(cuda(y)).cpu().numpy()
+  assert np.max(np.abs(back - back_legacy)) < 2e-6
 
 
 def test_kernels_really_launched():
