@@ -372,6 +372,101 @@ mdct_inverse_tile_kernel(MdctDeviceTables tb, const float* __restrict__ y, const
   if (tid == 0) bulk_wait<0>();
 }
 
+// Plain inverse (no fused dequantisation): the amplitudes are the only input, so the second tile buffer that the
+// dequantising kernel spends on the integers is free to double-buffer the bulk loads, and the overlap-add writes
+// its output blocks straight to global memory (coalesced 8-byte stores) instead of staging them.
+template <typename Plan, int C, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+mdct_inverse_plain_tile_kernel(MdctDeviceTables tb, const float* __restrict__ y, float* __restrict__ x, int frames_n,
+                               int tiles_per_row, int64_t total_tiles) {
+  using S = TileShape<Plan, C, THREADS>;
+  constexpr int M = S::M, N = S::N, H = M, T = S::T, E = Plan::E, FP = S::FP, ROW = S::ROW;
+  constexpr int BUF = FP * ROW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* bufs = reinterpret_cast<float*>(smem_raw);                  // [2][FP][ROW]: amplitudes -> scratch -> v
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(bufs + 2 * BUF);      // [2]
+
+  const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = (tid >> 3) & 1;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue_load = [&](int64_t tile, int slot) {        // thread 0 only
+    const int64_t b = tile / tiles_per_row;
+    const int fs = static_cast<int>(tile - b * tiles_per_row) * (FP - 1) - 1;
+    const int r_lo = fs < 0 ? 1 : 0;
+    const int r_hi = min(FP, frames_n - fs);
+    if (r_hi > r_lo) {
+      const uint32_t bytes = static_cast<uint32_t>(r_hi - r_lo) * ROW * sizeof(float);
+      mbar_arrive_expect_tx(&mbar[slot], bytes);
+      bulk_load(bufs + slot * BUF + r_lo * ROW, y + (b * frames_n + (fs + r_lo)) * static_cast<int64_t>(ROW), bytes, &mbar[slot]);
+    } else {
+      mbar_arrive(&mbar[slot]);
+    }
+  };
+  if (tid == 0 && blockIdx.x < total_tiles) issue_load(blockIdx.x, 0);
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int slot = it & 1;
+    float* abuf = bufs + slot * BUF;
+    float* arow = abuf + g * (2 / C) * ROW;
+    const int64_t b = tile / tiles_per_row;
+    const int nb0 = static_cast<int>(tile - b * tiles_per_row) * (FP - 1);   // first output block
+    const int fs = nb0 - 1;
+    const int r_lo = fs < 0 ? 1 : 0;
+    const int r_hi = min(FP, frames_n - fs);
+    // the other buffer was last read by the overlap-add of the previous tile, which ended in a block-wide barrier
+    if (tid == 0 && tile + gridDim.x < total_tiles) issue_load(tile + gridDim.x, slot ^ 1);
+    mbar_wait(&mbar[slot], (it >> 1) & 1);
+    if (r_lo > 0 || r_hi < FP) {               // frames outside the signal are zero (mdctransformer.py:366)
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r_lo > 0)
+        for (int i = tid * 4; i < ROW; i += THREADS * 4) *reinterpret_cast<float4*>(abuf + i) = z;
+      for (int i = max(r_hi, r_lo) * ROW + tid * 4; i < BUF; i += THREADS * 4) *reinterpret_cast<float4*>(abuf + i) = z;
+      __syncthreads();
+    }
+
+    float2 v0[E], v1[E];
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+      const int n = Plan::in_index(t, s);
+      const int a1 = variant ? N - 1 - 2 * n : 2 * n;
+      const int a2 = (N - 1) - a1;
+      const float2 l1 = ld2<C, ROW>(arow, a1), l2 = ld2<C, ROW>(arow, a2);
+      const float4 k4 = __ldg(&tb.pre_inv[variant * M + n]);
+      v0[s] = make_float2(fmaf(l2.x, k4.y, l1.x * k4.x), fmaf(l2.x, k4.w, l1.x * k4.z));
+      v1[s] = make_float2(fmaf(l2.y, k4.y, l1.y * k4.x), fmaf(l2.y, k4.w, l1.y * k4.z));
+    }
+    group_sync<T>(g);
+    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(arow), t, g, tb.tw_pass1, tb.tw_pass2);
+    post_store<Plan, C, ROW>(v0, v1, arow, t, variant, tb.post_inv);
+    __syncthreads();
+
+    const int nblk = min(FP - 1, frames_n + 1 - nb0);
+    float* xb = x + (b * (frames_n + 1) + nb0) * static_cast<int64_t>(ROW);
+    for (int idx = tid; idx < nblk * H; idx += THREADS) {
+      const int bl = idx / H, p = idx % H;
+      const float4 s = __ldg(&tb.unfold[p]);
+      const float* vn = abuf + (bl + 1) * ROW + (H - 1 - p) * C;
+      const float* vp = abuf + bl * ROW + (H + p) * C;
+      float* xo = xb + static_cast<int64_t>(bl) * ROW;
+      if constexpr (C == 2) {
+        const float2 a = *reinterpret_cast<const float2*>(vn), c = *reinterpret_cast<const float2*>(vp);
+        *reinterpret_cast<float2*>(xo + 2 * p) = make_float2(fmaf(s.x, a.x, s.y * c.x), fmaf(s.x, a.y, s.y * c.y));
+        *reinterpret_cast<float2*>(xo + 2 * (N - 1 - p)) = make_float2(fmaf(s.z, a.x, s.w * c.x), fmaf(s.z, a.y, s.w * c.y));
+      } else {
+        xo[p] = fmaf(s.x, vn[0], s.y * vp[0]);
+        xo[N - 1 - p] = fmaf(s.z, vn[0], s.w * vp[0]);
+      }
+    }
+    __syncthreads();       // this buffer is the target of the bulk load issued at the top of the next iteration
+  }
+}
+
 // ------------------------------------------------------------------------------------------ launchers
 template <typename Plan, int C, int THREADS, int MINB>
 cudaError_t launch_forward_tile(const MdctDeviceTables& tb, const float* x, float* y, int64_t batches, int blocks_n,
@@ -410,10 +505,10 @@ cudaError_t launch_inverse_tile(const MdctDeviceTables& tb, const float* y, cons
     if (err != cudaSuccess) return err;
     kernel<<<grid, THREADS, smem, stream>>>(tb, y, q, thr, x, frames_n, tiles_per_row, total);
   } else {
-    auto kernel = mdct_inverse_tile_kernel<Plan, C, THREADS, MINB, false>;
+    auto kernel = mdct_inverse_plain_tile_kernel<Plan, C, THREADS, MINB>;
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    kernel<<<grid, THREADS, smem, stream>>>(tb, y, q, thr, x, frames_n, tiles_per_row, total);
+    kernel<<<grid, THREADS, smem, stream>>>(tb, y, x, frames_n, tiles_per_row, total);
   }
   count_launch();
   return cudaGetLastError();
