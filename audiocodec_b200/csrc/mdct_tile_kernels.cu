@@ -22,6 +22,7 @@
 #include "async_copy.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace ac {
 
@@ -254,70 +255,81 @@ mdct_forward_tile_kernel(MdctDeviceTables tb, const float* __restrict__ x, float
 // ------------------------------------------------------------------------------------------ inverse
 // A tile transforms FP consecutive frames (the first one is the halo: frame nb0 - 1) and emits the FP - 1
 // output blocks nb0 .. nb0 + FP - 2, each of which needs two adjacent frames (TDAC overlap-add, H_inv).
-template <typename Plan, int C, int THREADS, int MINB, bool DEQUANT>
+//
+// Dequantising inverse, fully overlapped loads: the steps are double-buffered, the integers have one buffer that
+// is re-armed as soon as every thread has consumed them, and the output goes straight to global memory.  96 KB of
+// shared memory per CTA at N = 256 (two CTAs per SM): the kernel is nowhere near issue-bound, so eight warps are
+// enough, and no CTA waits for a tile (single-buffered, 38 % of the stall samples sat in the mbarrier wait).
+template <typename Plan, int C, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-mdct_inverse_tile_kernel(MdctDeviceTables tb, const float* __restrict__ y, const int32_t* __restrict__ q,
-                         const float* __restrict__ thr, float* __restrict__ x, int frames_n, int tiles_per_row,
-                         int64_t total_tiles) {
+mdct_inverse_dequant_tile_kernel(MdctDeviceTables tb, const int32_t* __restrict__ q, const float* __restrict__ thr,
+                                 float* __restrict__ x, int frames_n, int tiles_per_row, int64_t total_tiles) {
   using S = TileShape<Plan, C, THREADS>;
   constexpr int M = S::M, N = S::N, H = M, T = S::T, E = Plan::E, FP = S::FP, ROW = S::ROW;
+  constexpr int BUF = FP * ROW;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  float* abuf = reinterpret_cast<float*>(smem_raw);      // [FP][ROW]: amplitudes / steps -> scratch -> v = sqrt(4N) DCT-IV
-  float* bbuf = abuf + FP * ROW;                         // [FP][ROW]: quantised integers -> output blocks
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(bbuf + FP * ROW);
+  float* tbufs = reinterpret_cast<float*>(smem_raw);                 // [2][FP][ROW]: steps -> scratch -> v
+  float* qbuf = tbufs + 2 * BUF;                                     // [FP][ROW]: quantised integers
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(qbuf + BUF);          // [0..1] steps, [2] integers
 
   const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = (tid >> 3) & 1;
-  float* arow = abuf + g * (2 / C) * ROW;
-  const int32_t* qrow = reinterpret_cast<const int32_t*>(bbuf) + g * (2 / C) * ROW;
+  const int32_t* qrow = reinterpret_cast<const int32_t*>(qbuf) + g * (2 / C) * ROW;
   if (tid == 0) {
-    mbar_init(mbar, 1);
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_init(&mbar[2], 1);
     mbar_fence_init();
   }
   __syncthreads();
-  uint32_t parity = 0;
 
-  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+  auto issue_load = [&](int64_t tile, float* dst, const void* src, uint64_t* bar) {        // thread 0 only
     const int64_t b = tile / tiles_per_row;
-    const int nb0 = static_cast<int>(tile - b * tiles_per_row) * (FP - 1);   // first output block
-    const int fs = nb0 - 1;                                                   // first frame of the tile
+    const int fs = static_cast<int>(tile - b * tiles_per_row) * (FP - 1) - 1;
     const int r_lo = fs < 0 ? 1 : 0;
     const int r_hi = min(FP, frames_n - fs);
     if (r_hi > r_lo) {
-      if (tid == 0) {
-        bulk_wait_read<0>();
-        const uint32_t bytes = static_cast<uint32_t>(r_hi - r_lo) * ROW * sizeof(float);
-        const int64_t off = (b * frames_n + (fs + r_lo)) * static_cast<int64_t>(ROW);
-        if (DEQUANT) {
-          mbar_arrive_expect_tx(mbar, 2 * bytes);
-          bulk_load(abuf + r_lo * ROW, thr + off, bytes, mbar);
-          bulk_load(bbuf + r_lo * ROW, q + off, bytes, mbar);
-        } else {
-          mbar_arrive_expect_tx(mbar, bytes);
-          bulk_load(abuf + r_lo * ROW, y + off, bytes, mbar);
-        }
-      }
-      mbar_wait(mbar, parity);
-      parity ^= 1;
+      const uint32_t bytes = static_cast<uint32_t>(r_hi - r_lo) * ROW * sizeof(float);
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_load(dst + r_lo * ROW, static_cast<const float*>(src) + (b * frames_n + (fs + r_lo)) * static_cast<int64_t>(ROW), bytes, bar);
     } else {
-      if (tid == 0) bulk_wait_read<0>();
-      __syncthreads();
+      mbar_arrive(bar);
     }
+  };
+  if (tid == 0 && blockIdx.x < total_tiles) {
+    issue_load(blockIdx.x, tbufs, thr, &mbar[0]);
+    issue_load(blockIdx.x, qbuf, q, &mbar[2]);
+  }
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int slot = it & 1;
+    float* abuf = tbufs + slot * BUF;
+    float* arow = abuf + g * (2 / C) * ROW;
+    const int64_t b = tile / tiles_per_row;
+    const int nb0 = static_cast<int>(tile - b * tiles_per_row) * (FP - 1);   // first output block
+    const int fs = nb0 - 1;
+    const int r_lo = fs < 0 ? 1 : 0;
+    const int r_hi = min(FP, frames_n - fs);
+    const bool more = tile + gridDim.x < total_tiles;
+    // the other step buffer was last read by the overlap-add of the previous tile, which ended in a barrier
+    if (tid == 0 && more) issue_load(tile + gridDim.x, tbufs + (slot ^ 1) * BUF, thr, &mbar[slot ^ 1]);
+    mbar_wait(&mbar[slot], (it >> 1) & 1);
+    mbar_wait(&mbar[2], it & 1);
     if (r_lo > 0 || r_hi < FP) {               // frames outside the signal are zero (mdctransformer.py:366)
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r_lo > 0)
         for (int i = tid * 4; i < ROW; i += THREADS * 4) {
           *reinterpret_cast<float4*>(abuf + i) = z;
-          if (DEQUANT) *reinterpret_cast<float4*>(bbuf + i) = z;
+          *reinterpret_cast<float4*>(qbuf + i) = z;
         }
-      const int z0 = max(r_hi, r_lo) * ROW;
-      for (int i = z0 + tid * 4; i < FP * ROW; i += THREADS * 4) {
+      for (int i = max(r_hi, r_lo) * ROW + tid * 4; i < BUF; i += THREADS * 4) {
         *reinterpret_cast<float4*>(abuf + i) = z;
-        if (DEQUANT) *reinterpret_cast<float4*>(bbuf + i) = z;
+        *reinterpret_cast<float4*>(qbuf + i) = z;
       }
       __syncthreads();
     }
 
-    // ---- (dequantise,) pre-twiddle                                                 (mdctransformer.py:141-148)
+    // ---- dequantise, pre-twiddle                                                   (mdctransformer.py:141-148)
     float2 v0[E], v1[E];
 #pragma unroll
     for (int s = 0; s < E; ++s) {
@@ -325,33 +337,32 @@ mdct_inverse_tile_kernel(MdctDeviceTables tb, const float* __restrict__ y, const
       const int a1 = variant ? N - 1 - 2 * n : 2 * n;
       const int a2 = (N - 1) - a1;
       float2 l1 = ld2<C, ROW>(arow, a1), l2 = ld2<C, ROW>(arow, a2);
-      if (DEQUANT) {
-        const float2 q1 = ld2<C, ROW>(reinterpret_cast<const float*>(qrow), a1);
-        const float2 q2 = ld2<C, ROW>(reinterpret_cast<const float*>(qrow), a2);
-        l1.x *= static_cast<float>(__float_as_int(q1.x));
-        l1.y *= static_cast<float>(__float_as_int(q1.y));
-        l2.x *= static_cast<float>(__float_as_int(q2.x));
-        l2.y *= static_cast<float>(__float_as_int(q2.y));
-      }
+      const float2 q1 = ld2<C, ROW>(reinterpret_cast<const float*>(qrow), a1);
+      const float2 q2 = ld2<C, ROW>(reinterpret_cast<const float*>(qrow), a2);
+      l1.x *= static_cast<float>(__float_as_int(q1.x));
+      l1.y *= static_cast<float>(__float_as_int(q1.y));
+      l2.x *= static_cast<float>(__float_as_int(q2.x));
+      l2.y *= static_cast<float>(__float_as_int(q2.y));
       const float4 k4 = __ldg(&tb.pre_inv[variant * M + n]);
       v0[s] = make_float2(fmaf(l2.x, k4.y, l1.x * k4.x), fmaf(l2.x, k4.w, l1.x * k4.z));
       v1[s] = make_float2(fmaf(l2.y, k4.y, l1.y * k4.x), fmaf(l2.y, k4.w, l1.y * k4.z));
     }
-    group_sync<T>(g);                           // the group's rows have been read: they become its scratch
+    __syncthreads();                           // integers consumed by everybody: their buffer takes the next tile
+    if (tid == 0 && more) issue_load(tile + gridDim.x, qbuf, q, &mbar[2]);
 
     fft2<Plan>(v0, v1, reinterpret_cast<float4*>(arow), t, g, tb.tw_pass1, tb.tw_pass2);
     post_store<Plan, C, ROW>(v0, v1, arow, t, variant, tb.post_inv);
     __syncthreads();
 
-    // ---- synthesis window + TDAC overlap-add (H_inv, mdctransformer.py:148,176-190): block i of the tile takes
-    //      the lower half of v of frame i + 1 and the upper half of v of frame i
-    constexpr int PAIRS = (FP - 1) * H;
-    for (int idx = tid; idx < PAIRS; idx += THREADS) {
+    // ---- synthesis window + TDAC overlap-add (H_inv, mdctransformer.py:148,176-190), straight to global memory
+    const int nblk = min(FP - 1, frames_n + 1 - nb0);
+    float* xb = x + (b * (frames_n + 1) + nb0) * static_cast<int64_t>(ROW);
+    for (int idx = tid; idx < nblk * H; idx += THREADS) {
       const int bl = idx / H, p = idx % H;
       const float4 s = __ldg(&tb.unfold[p]);
       const float* vn = abuf + (bl + 1) * ROW + (H - 1 - p) * C;
       const float* vp = abuf + bl * ROW + (H + p) * C;
-      float* xo = bbuf + bl * ROW;
+      float* xo = xb + static_cast<int64_t>(bl) * ROW;
       if constexpr (C == 2) {
         const float2 a = *reinterpret_cast<const float2*>(vn), c = *reinterpret_cast<const float2*>(vp);
         *reinterpret_cast<float2*>(xo + 2 * p) = make_float2(fmaf(s.x, a.x, s.y * c.x), fmaf(s.x, a.y, s.y * c.y));
@@ -361,15 +372,8 @@ mdct_inverse_tile_kernel(MdctDeviceTables tb, const float* __restrict__ y, const
         xo[N - 1 - p] = fmaf(s.z, vn[0], s.w * vp[0]);
       }
     }
-    fence_async_smem();
-    __syncthreads();
-    if (tid == 0) {
-      const int nblk = min(FP - 1, frames_n + 1 - nb0);
-      bulk_store(x + (b * (frames_n + 1) + nb0) * static_cast<int64_t>(ROW), bbuf, static_cast<uint32_t>(nblk) * ROW * sizeof(float));
-      bulk_commit();
-    }
+    __syncthreads();       // this step buffer is the target of the bulk load issued at the top of the next iteration
   }
-  if (tid == 0) bulk_wait<0>();
 }
 
 // Plain inverse (no fused dequantisation): the amplitudes are the only input, so the second tile buffer that the
@@ -491,7 +495,9 @@ cudaError_t launch_inverse_tile(const MdctDeviceTables& tb, const float* y, cons
                                 int64_t batches, int frames_n, cudaStream_t stream) {
   using S = TileShape<Plan, C, THREADS>;
   static_assert(S::FP >= 2, "an inverse tile needs two frames");
-  const size_t smem = static_cast<size_t>(2 * S::FP) * S::ROW * sizeof(float) + 16;
+  const int buffers = q != nullptr ? 3 : 2;          // steps x 2 + integers, or amplitudes x 2
+  const size_t smem = static_cast<size_t>(buffers * S::FP) * S::ROW * sizeof(float) + 32;
+  if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
   const int tiles_per_row = (frames_n + 1 + S::FP - 2) / (S::FP - 1);
   const int64_t total = batches * tiles_per_row;
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
@@ -500,10 +506,13 @@ cudaError_t launch_inverse_tile(const MdctDeviceTables& tb, const float* y, cons
   const unsigned grid = static_cast<unsigned>(std::min(total, cap));
   cudaError_t err;
   if (q != nullptr) {
-    auto kernel = mdct_inverse_tile_kernel<Plan, C, THREADS, MINB, true>;
+    // the register budget follows the CTAs that actually fit: three tile buffers often allow fewer than MINB
+    constexpr int kFit = static_cast<int>((227 * 1024) / (3 * S::FP * S::ROW * sizeof(float) + 32 + 1024));
+    constexpr int kMinB = kFit < 1 ? 1 : (kFit < MINB ? kFit : MINB);
+    auto kernel = mdct_inverse_dequant_tile_kernel<Plan, C, THREADS, kMinB>;
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    kernel<<<grid, THREADS, smem, stream>>>(tb, y, q, thr, x, frames_n, tiles_per_row, total);
+    kernel<<<grid, THREADS, smem, stream>>>(tb, q, thr, x, frames_n, tiles_per_row, total);
   } else {
     auto kernel = mdct_inverse_plain_tile_kernel<Plan, C, THREADS, MINB>;
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
