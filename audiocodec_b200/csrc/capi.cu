@@ -82,6 +82,7 @@ struct ac_mdct_plan {
 struct ac_pa_plan {
   int device = 0;
   ac::PaDeviceTables tb;
+  ac::PaJobParams jobs;
   ac::PaTables host;
   std::vector<void*> owned;
 };
@@ -418,6 +419,73 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
   desc_start[static_cast<size_t>(d.n_chunks) * 5] = static_cast<int32_t>(band_desc.size());
   d.n_desc = static_cast<int>(band_desc.size());
   d.n_band_w4 = static_cast<int>(band_w4.size());
+  // ---- tensor-core tile kernel: the same steps grouped into one job per (band, chunk); a warp runs whole jobs
+  std::vector<int4> job_desc;
+  std::vector<int32_t> job_start(static_cast<size_t>(d.n_chunks) * 9 + 1, 0);
+  {
+    size_t sidx = 0;
+    for (int c = 0; c < d.n_chunks; ++c) {
+      const size_t chunk_end = desc_start[static_cast<size_t>(c) * 5 + 4];
+      const size_t first_job = job_desc.size();
+      std::vector<double> cost;
+      while (sidx < chunk_end) {
+        const int4 first = band_desc[sidx];
+        int steps = 0;
+        while (!(band_desc[sidx + steps].z & 0x800)) ++steps;
+        ++steps;
+        int4 jb;
+        const int band = first.z & 0xff;
+        jb.x = first.x * 66 * 4;                         // byte offset of the first row of T (66 words per row)
+        jb.y = first.y * 8;                              // byte offset of the weights, each stored twice (packed pairs)
+        jb.z = steps;
+        // byte offset of P[band][0] (64 items per band) with the XOR swizzle of the band folded in (the kernel xors
+        // 8 * lane: a lane owns the item pair 2 lane, 2 lane + 1)
+        jb.w = (band * 256 + ((band & 3) << 5)) | ((first.z & 0x100) ? 0x10000 : 0) | ((first.z & 0x200) ? 0x20000 : 0);
+        job_desc.push_back(jb);
+        cost.push_back(12.5 * steps + ((first.z & 0x200) ? 45.0 : 25.0));   // ~instructions per lane
+        sidx += static_cast<size_t>(steps);
+      }
+      double total = 0, run = 0;
+      for (double v : cost) total += v;
+      int w = 0;
+      job_start[static_cast<size_t>(c) * 9] = static_cast<int32_t>(first_job);
+      for (size_t j = 0; j < cost.size(); ++j) {
+        run += cost[j];
+        while (w < 7 && run >= total * (w + 1) / 8.0)
+          job_start[static_cast<size_t>(c) * 9 + (++w)] = static_cast<int32_t>(first_job + j + 1);
+      }
+      while (w < 8) job_start[static_cast<size_t>(c) * 9 + (++w)] = static_cast<int32_t>(job_desc.size());
+    }
+    job_start[static_cast<size_t>(d.n_chunks) * 9] = static_cast<int32_t>(job_desc.size());
+  }
+  d.n_jobs = static_cast<int>(job_desc.size());
+  if (d.n_jobs <= ac::kPaMaxJobs && d.n_chunks <= ac::kPaMaxChunks) {
+    std::memset(&plan->jobs, 0, sizeof(plan->jobs));
+    std::copy(job_desc.begin(), job_desc.end(), plan->jobs.job);
+    std::copy(job_start.begin(), job_start.end(), plan->jobs.start);
+    d.jobs_host = &plan->jobs;
+  }
+  auto pow_table = [](float a) {
+    std::vector<float2> tab(256);
+    for (int e = 0; e < 256; ++e) {
+      if (e == 255) {
+        tab[e] = make_float2(INFINITY, 0.f);
+        continue;
+      }
+      const double ae = static_cast<double>(a) * (e - 127);
+      const double nr = std::nearbyint(ae);
+      tab[e] = make_float2(static_cast<float>(std::ldexp(1.0, static_cast<int>(nr))), static_cast<float>(ae - nr));
+    }
+    return tab;
+  };
+  const std::vector<float2> pow_alpha = pow_table(d.alpha), pow_inv_alpha = pow_table(d.inv_alpha);
+  d.offset_log2 = static_cast<float>(-std::log2(10.0) / 10.0);
+  {
+    // max(eps, masking)^(1/alpha) <= eps when alpha <= 1; the result is then raised to the quiet threshold anyway
+    float quiet_min = INFINITY;
+    for (double qv : t.quiet) quiet_min = std::min(quiet_min, static_cast<float>(qv));
+    d.clamp_needed = (alpha <= 1.0 && quiet_min >= d.eps) ? 0 : 1;
+  }
   std::vector<float4> filt4(t.n, make_float4(0.f, 0.f, 0.f, 0.f));
   if (d.tile_ok) {
     for (int k = 0; k < t.n; ++k) {
@@ -444,7 +512,9 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
       (err = upload(band_desc, &d.band_desc, plan->owned)) != cudaSuccess ||
       (err = upload(band_w4, &d.band_w4, plan->owned)) != cudaSuccess ||
       (err = upload(desc_start, &d.desc_start, plan->owned)) != cudaSuccess ||
-      (err = upload(filt4, &d.filt4, plan->owned)) != cudaSuccess) {
+      (err = upload(filt4, &d.filt4, plan->owned)) != cudaSuccess ||
+      (err = upload(pow_alpha, &d.pow_alpha, plan->owned)) != cudaSuccess ||
+      (err = upload(pow_inv_alpha, &d.pow_inv_alpha, plan->owned)) != cudaSuccess) {
     free_all(plan->owned);
     delete plan;
     return cuda_fail(err, "uploading psychoacoustic tables");

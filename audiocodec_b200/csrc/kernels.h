@@ -42,6 +42,15 @@ inline bool tile_fft_radices(int n, int* r0, int* r1, int* r2) {
   }
 }
 
+// Band-sum job list of the tensor-core tile kernel, passed BY VALUE as a kernel parameter: it then lives in the
+// constant bank, job descriptors and loop bounds are read through the uniform datapath and every branch on them is
+// warp-uniform by construction (no convergence barriers, no shared-memory traffic for control).
+constexpr int kPaMaxJobs = 160, kPaMaxChunks = 16;
+struct PaJobParams {
+  int4 job[kPaMaxJobs];
+  int32_t start[9 * kPaMaxChunks + 1];
+};
+
 // Device-resident psychoacoustic tables (psychoacoustic.py:52-69, sparse forms from tables.h).
 struct PaDeviceTables {
   int n = 0, nb = 0;
@@ -74,7 +83,27 @@ struct PaDeviceTables {
   const int32_t* desc_start = nullptr;
   const float4* filt4 = nullptr;
   float gain_log2 = 0.f;    // fp32(-alpha * log2(10) / 10): gain = 2^(gain_log2 * offset)   (psychoacoustic.py:197)
+  // tensor-core tile kernel (psycho_mma_kernels.cu):
+  //   jobs_host->job[j] = one bark band inside one chunk: { byte offset of its first row of T (66 words per row), byte
+  //                 offset of its (zero-padded, duplicated) weights, steps of four filters, byte offset of P[band] (64
+  //                 items per band, XOR swizzle (band & 3) << 3 items folded in) | add-earlier-partial << 16 |
+  //                 band-complete << 17 }
+  //   jobs_host->start[9 c + w] .. start[9 c + w + 1]: the jobs warp w of an 8-warp CTA runs in chunk c (9 entries per chunk)
+  //   pow_alpha[E] / pow_inv_alpha[E], E = biased exponent of x: { 2^rint(a (E - 127)), a (E - 127) - rint(a (E - 127)) },
+  //                 so that x^a = 2^(a log2(mantissa) + second) * first with full fp32 precision in the exponent
+  int n_jobs = 0;
+  int clamp_needed = 1;     // 0: max(eps, .) before ^(1/alpha) can never win against the quiet threshold
+  const PaJobParams* jobs_host = nullptr;   // HOST pointer (owned by the plan); null when the list does not fit
+  const float2* pow_alpha = nullptr;
+  const float2* pow_inv_alpha = nullptr;
+  float offset_log2 = 0.f;  // fp32(-log2(10) / 10) = gain_log2 / alpha: the masking offset in the log2 domain after ^(1/alpha)
 };
+
+// psycho_mma_kernels.cu: nb == 64, <= 3 bands per filter, 1 / 2 / 4 channels
+bool pa_mma_tile_supported(const PaDeviceTables& tb, int channels);
+cudaError_t pa_threshold_mma_tile(const PaDeviceTables& tb, const float* y, const float* ton_in, float one_minus_drown,
+                                  float thr_scale, float* thr_out, int32_t* q_out, int64_t frames, int channels,
+                                  cudaStream_t stream);
 
 void count_launch();
 int tile_sm_count();

@@ -231,3 +231,28 @@ def test_quantizer_odd_sizes_take_the_scalar_kernel():
     q = pa.quantize(cuda(y), cuda(thr))
     assert np.array_equal(q.cpu().numpy(), oracle.quantize(y, thr))
     assert np.array_equal(pa.dequantize(q, cuda(thr)).cpu().numpy(), oracle.dequantize(q.cpu().numpy(), thr))
+
+
+# ---- tensor-core tile kernel against the first-generation (fp32 FMA) tile kernel and the generic kernel ------
+@pytest.mark.parametrize("sr,n,c,b,m", [(44100, 256, 2, 3, 37), (44100, 256, 1, 2, 70), (44100, 256, 4, 2, 11),
+                                        (48000, 1024, 2, 2, 19), (44100, 64, 2, 2, 33), (44100, 128, 1, 1, 40),
+                                        (44100, 512, 2, 1, 18), (44100, 320, 2, 2, 9), (48000, 2048, 1, 1, 5)])
+def test_mma_tile_kernel_against_other_kernels(sr, n, c, b, m, monkeypatch):
+  rng = np.random.default_rng(7 * n + c)
+  y = cuda((rng.standard_normal((b, m, n, c)) * 10.0 ** rng.uniform(-5, 0, (b, m, n, c))).astype(np.float32))
+  pa = audiocodec_b200.PsychoacousticModel(sr, n)
+  out = {}
+  for kernel in ("mma", "fma", "generic"):
+    monkeypatch.setenv("AC_PA_KERNEL", kernel)
+    q, step = pa.encode(y, thr_scale=1.5, drown=0.25)
+    thr = pa.global_masking_threshold(y, pa.tonality(y), drown=0.25)
+    torch.cuda.synchronize()
+    out[kernel] = (q.cpu().numpy(), step.cpu().numpy(), thr.cpu().numpy())
+    assert torch.equal(q, pa.quantize(y, step))             # the fused division is the IEEE one
+  monkeypatch.delenv("AC_PA_KERNEL")
+  for other in ("fma", "generic"):
+    np.testing.assert_allclose(out["mma"][1], out[other][1], rtol=5e-6)
+    np.testing.assert_allclose(out["mma"][2], out[other][2], rtol=5e-6)
+    diff = np.abs(out["mma"][0].astype(np.int64) - out[other][0])
+    assert diff.max() <= 1 and np.mean(diff == 0) >= 0.999
+  np.testing.assert_allclose(out["mma"][1], 1.5 * out["mma"][2], rtol=2e-6)
