@@ -419,31 +419,34 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
   desc_start[static_cast<size_t>(d.n_chunks) * 5] = static_cast<int32_t>(band_desc.size());
   d.n_desc = static_cast<int>(band_desc.size());
   d.n_band_w4 = static_cast<int>(band_w4.size());
-  // ---- tensor-core tile kernel: the same steps grouped into one job per (band, chunk); a warp runs whole jobs
-  std::vector<int4> job_desc;
-  std::vector<int32_t> job_start(static_cast<size_t>(d.n_chunks) * 9 + 1, 0);
+  // ---- tensor-core tile kernel: chunks of 64 filters, one job per (band, chunk) = steps of four filters with
+  //      zero-padded weights; the jobs of a chunk are dealt to the eight warps in contiguous runs of equal cost
+  std::vector<float> mma_w4;
   {
-    size_t sidx = 0;
-    for (int c = 0; c < d.n_chunks; ++c) {
-      const size_t chunk_end = desc_start[static_cast<size_t>(c) * 5 + 4];
+    d.mma_chunk_k = 64;
+    d.mma_n_chunks = (t.n + d.mma_chunk_k - 1) / d.mma_chunk_k;
+    std::vector<int4> job_desc;
+    std::vector<int32_t> job_start(static_cast<size_t>(d.mma_n_chunks) * 9 + 1, 0);
+    for (int c = 0; c < d.mma_n_chunks; ++c) {
+      const int kc0 = c * d.mma_chunk_k, kc1 = std::min(t.n, kc0 + d.mma_chunk_k);
       const size_t first_job = job_desc.size();
       std::vector<double> cost;
-      while (sidx < chunk_end) {
-        const int4 first = band_desc[sidx];
-        int steps = 0;
-        while (!(band_desc[sidx + steps].z & 0x800)) ++steps;
-        ++steps;
+      for (int i = 0; i < t.nb; ++i) {
+        const int ka = std::max(t.band_k0[i], kc0), kb = std::min(t.band_k0[i] + t.band_cnt[i], kc1);
+        if (kb <= ka) continue;
+        const int steps = (kb - ka + 3) / 4;
+        const bool final = t.band_k0[i] + t.band_cnt[i] <= kc1, partial = t.band_k0[i] < kc0;
         int4 jb;
-        const int band = first.z & 0xff;
-        jb.x = first.x * 66 * 4;                         // byte offset of the first row of T (66 words per row)
-        jb.y = first.y * 8;                              // byte offset of the weights, each stored twice (packed pairs)
+        jb.x = (ka - kc0) * 66 * 4;                      // byte offset of the first row of T (66 words per row)
+        jb.y = static_cast<int>(mma_w4.size()) * 8;      // byte offset of the weights, each stored twice (packed pairs)
         jb.z = steps;
         // byte offset of P[band][0] (64 items per band) with the XOR swizzle of the band folded in (the kernel xors
         // 8 * lane: a lane owns the item pair 2 lane, 2 lane + 1)
-        jb.w = (band * 256 + ((band & 3) << 5)) | ((first.z & 0x100) ? 0x10000 : 0) | ((first.z & 0x200) ? 0x20000 : 0);
+        jb.w = (i * 256 + ((i & 3) << 5)) | (partial ? 0x10000 : 0) | (final ? 0x20000 : 0);
+        for (int k = ka; k < ka + 4 * steps; ++k)
+          mma_w4.push_back(k < kb ? t.band_w[t.band_ptr[i] + (k - t.band_k0[i])] : 0.f);
         job_desc.push_back(jb);
-        cost.push_back(12.5 * steps + ((first.z & 0x200) ? 45.0 : 25.0));   // ~instructions per lane
-        sidx += static_cast<size_t>(steps);
+        cost.push_back(13.5 * steps + (final ? 45.0 : 25.0));   // ~instructions per lane
       }
       double total = 0, run = 0;
       for (double v : cost) total += v;
@@ -456,14 +459,15 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
       }
       while (w < 8) job_start[static_cast<size_t>(c) * 9 + (++w)] = static_cast<int32_t>(job_desc.size());
     }
-    job_start[static_cast<size_t>(d.n_chunks) * 9] = static_cast<int32_t>(job_desc.size());
-  }
-  d.n_jobs = static_cast<int>(job_desc.size());
-  if (d.n_jobs <= ac::kPaMaxJobs && d.n_chunks <= ac::kPaMaxChunks) {
-    std::memset(&plan->jobs, 0, sizeof(plan->jobs));
-    std::copy(job_desc.begin(), job_desc.end(), plan->jobs.job);
-    std::copy(job_start.begin(), job_start.end(), plan->jobs.start);
-    d.jobs_host = &plan->jobs;
+    job_start[static_cast<size_t>(d.mma_n_chunks) * 9] = static_cast<int32_t>(job_desc.size());
+    d.n_jobs = static_cast<int>(job_desc.size());
+    d.n_mma_w4 = static_cast<int>(mma_w4.size());
+    if (d.n_jobs <= ac::kPaMaxJobs && d.mma_n_chunks <= ac::kPaMaxChunks) {
+      std::memset(&plan->jobs, 0, sizeof(plan->jobs));
+      std::copy(job_desc.begin(), job_desc.end(), plan->jobs.job);
+      std::copy(job_start.begin(), job_start.end(), plan->jobs.start);
+      d.jobs_host = &plan->jobs;
+    }
   }
   auto pow_table = [](float a) {
     std::vector<float2> tab(256);
@@ -495,6 +499,9 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
       float b0f;
       std::memcpy(&b0f, &b0, sizeof(float));
       filt4[k] = make_float4(w3[0], w3[1], w3[2], b0f);
+      if (k / 32 < 64)
+        for (int sl = 0; sl < 3; ++sl)
+          if (w3[sl] != 0.f) d.filt_mask[k / 32] |= static_cast<uint8_t>(1u << sl);
     }
   }
   std::vector<float> quiet(t.quiet.begin(), t.quiet.end()), spread(t.spread_fn.begin(), t.spread_fn.end());
@@ -513,6 +520,7 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
       (err = upload(band_w4, &d.band_w4, plan->owned)) != cudaSuccess ||
       (err = upload(desc_start, &d.desc_start, plan->owned)) != cudaSuccess ||
       (err = upload(filt4, &d.filt4, plan->owned)) != cudaSuccess ||
+      (err = upload(mma_w4, &d.mma_w4, plan->owned)) != cudaSuccess ||
       (err = upload(pow_alpha, &d.pow_alpha, plan->owned)) != cudaSuccess ||
       (err = upload(pow_inv_alpha, &d.pow_inv_alpha, plan->owned)) != cudaSuccess) {
     free_all(plan->owned);

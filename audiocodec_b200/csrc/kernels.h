@@ -45,7 +45,7 @@ inline bool tile_fft_radices(int n, int* r0, int* r1, int* r2) {
 // Band-sum job list of the tensor-core tile kernel, passed BY VALUE as a kernel parameter: it then lives in the
 // constant bank, job descriptors and loop bounds are read through the uniform datapath and every branch on them is
 // warp-uniform by construction (no convergence barriers, no shared-memory traffic for control).
-constexpr int kPaMaxJobs = 160, kPaMaxChunks = 16;
+constexpr int kPaMaxJobs = 112, kPaMaxChunks = 32;
 struct PaJobParams {
   int4 job[kPaMaxJobs];
   int32_t start[9 * kPaMaxChunks + 1];
@@ -83,7 +83,7 @@ struct PaDeviceTables {
   const int32_t* desc_start = nullptr;
   const float4* filt4 = nullptr;
   float gain_log2 = 0.f;    // fp32(-alpha * log2(10) / 10): gain = 2^(gain_log2 * offset)   (psychoacoustic.py:197)
-  // tensor-core tile kernel (psycho_mma_kernels.cu):
+  // tensor-core tile kernel (psycho_mma_kernels.cu): the filter axis is processed in chunks of mma_chunk_k filters
   //   jobs_host->job[j] = one bark band inside one chunk: { byte offset of its first row of T (66 words per row), byte
   //                 offset of its (zero-padded, duplicated) weights, steps of four filters, byte offset of P[band] (64
   //                 items per band, XOR swizzle (band & 3) << 3 items folded in) | add-earlier-partial << 16 |
@@ -91,7 +91,10 @@ struct PaDeviceTables {
   //   jobs_host->start[9 c + w] .. start[9 c + w + 1]: the jobs warp w of an 8-warp CTA runs in chunk c (9 entries per chunk)
   //   pow_alpha[E] / pow_inv_alpha[E], E = biased exponent of x: { 2^rint(a (E - 127)), a (E - 127) - rint(a (E - 127)) },
   //                 so that x^a = 2^(a log2(mantissa) + second) * first with full fp32 precision in the exponent
-  int n_jobs = 0;
+  int n_jobs = 0, mma_chunk_k = 0, mma_n_chunks = 0, n_mma_w4 = 0;
+  const float* mma_w4 = nullptr;   // the (zero-padded) weights of the jobs' steps
+  // three bits per group of 32 filters: bit s set when a filter of the group has a non-zero filt4 weight for band slot s
+  uint8_t filt_mask[64] = {};
   int clamp_needed = 1;     // 0: max(eps, .) before ^(1/alpha) can never win against the quiet threshold
   const PaJobParams* jobs_host = nullptr;   // HOST pointer (owned by the plan); null when the list does not fit
   const float2* pow_alpha = nullptr;

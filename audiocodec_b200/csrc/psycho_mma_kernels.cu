@@ -24,6 +24,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 namespace ac {
 
@@ -36,7 +37,6 @@ constexpr int kTS = 66;       // row stride of T (words): 8-byte aligned item pa
 constexpr int kGS = 68;       // row stride of G: conflict-free stores from the accumulator layout (8 t + g), 16-byte rows
 constexpr int kPS = 64;       // row stride of P
 constexpr int kNB = 64;       // bark bands
-constexpr int kPartS = 65;    // row stride of the tonality partials
 
 template <int C> struct Vec;
 template <> struct Vec<1> { using F = float; using I = int32_t; };
@@ -137,30 +137,40 @@ __device__ __forceinline__ void sts_b64(uint32_t addr, u64 v) {
 }
 
 struct Layout2 {
-  int powa, powia, t, p, part, uv, sfh, sfl, quiet, lin, bw8, filt4, total;
+  int powa, powia, t, tbuf, p, part, uv, sfh, sfl, quiet, lin, bw8, filt4, total;
 };
 
 __host__ __device__ inline Layout2 layout2(const PaDeviceTables& tb) {
   Layout2 L;
-  const int kc = tb.n < tb.chunk_k ? tb.n : tb.chunk_k;
+  const int kc = tb.n < tb.mma_chunk_k ? tb.n : tb.mma_chunk_k;
   const int t_rows = (kc + 3) * kTS;                    // 3 zero rows behind the chunk for the 4-filter steps
-  const int g_words = kNB * kGS;                        // G aliases T (dead once the last band sum is done)
+  const int g_words = kNB * kGS;                        // G aliases the buffer of the tile's last chunk
   int o = 0;
   L.powa = o;    o += 512;                              // the exponent tables come first: an index with the sign bit
   L.powia = o;   o += 512;                              //   set (NaN input) still reads inside the allocation
-  L.t = o;       o += ((t_rows > g_words ? t_rows : g_words) + 3) & ~3;
+  L.tbuf = ((t_rows > g_words ? t_rows : g_words) + 3) & ~3;
+  L.t = o;       o += 2 * L.tbuf;                       // two chunk buffers: one is filled while the other is read
   L.p = o;       o += kNB * kPS;
-  L.part = o;    o += 8 * kPartS;
+  L.part = o;    o += 2 * kWarps * kTI;
   L.uv = o;      o += 3 * kTI;
   L.sfh = o;     o += 128;
   L.sfl = o;     o += 128;
   L.quiet = o;   o += kNB;
   L.lin = o;     o += kNB;
-  L.bw8 = o;     o += (2 * tb.n_band_w4 + 3) & ~3;       // every weight twice: a packed pair for both items of a lane
+  L.bw8 = o;     o += (2 * tb.n_mma_w4 + 3) & ~3;        // every weight twice: a packed pair for both items of a lane
   L.filt4 = o;   o += filt_in_smem(tb) ? 4 * tb.n : 0;   // long filter tables stay in global memory (L1 / L2)
   L.total = o;
   return L;
 }
+
+// asynchronous global -> shared copies of 4 or 8 bytes (LDGSTS): the destination address is free, so the copy
+// itself transposes y[frame][filter][channel] into T[filter][item]
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Phase D of the tile kernel for one frame row (all channels) per call: thr (and q) of the row's n filters.
 // G carries scale^2, so sqrt gives the scaled step directly; thr = v rsqrt(v) (relative error 2^-22), and the same
@@ -242,11 +252,88 @@ __device__ __forceinline__ void phase_d_row(const float4* __restrict__ filt4, co
   }
 }
 
+// The same for KI x 32 consecutive filters of a row with the filter-table entries f4[i] (filter k0 + 32 i + lane) held
+// in registers by the caller for all rows of the warp, and the y values yv[i] loaded by the caller.  masks: three bits
+// per 32-filter group, bit s set when any filter of the group has a non-zero weight for band slot s - the shared-memory
+// loads of unused slots are skipped (warp-uniform predicates; a skipped term is an exact + 0).
+template <int C, bool QUANT, bool THR, int KI>
+__device__ __forceinline__ void phase_d_unit(const float4 (&f4)[KI], const unsigned masks,
+                                             const typename Vec<C>::F (&yv)[KI], float* __restrict__ trow,
+                                             int32_t* __restrict__ qrow, const float* gr, const float eps_s2) {
+  using VF = typename Vec<C>::F;
+  using VI = typename Vec<C>::I;
+  constexpr int GS = kGS;
+  VF* tv = reinterpret_cast<VF*>(trow);
+  VI* qv = reinterpret_cast<VI*>(qrow);
+  const u64 k_neg = pack2(-1.f, -1.f);
+#pragma unroll
+  for (int i = 0; i < KI; ++i) {
+    const float* gp = gr + __float_as_int(f4[i].w) * GS;
+    const unsigned m = masks >> (3 * i);
+    if constexpr (C == 2) {
+      u64 v2 = 0ull;
+      if (m & 1u) v2 = fmul2(*reinterpret_cast<const u64*>(gp), pack2(f4[i].x, f4[i].x));
+      if (m & 2u) v2 = ffma2(*reinterpret_cast<const u64*>(gp + GS), pack2(f4[i].y, f4[i].y), v2);
+      if (m & 4u) v2 = ffma2(*reinterpret_cast<const u64*>(gp + 2 * GS), pack2(f4[i].z, f4[i].z), v2);
+      float vx, vy;
+      unpack2(v2, vx, vy);
+      vx = fmaxf(eps_s2, vx);
+      vy = fmaxf(eps_s2, vy);
+      const u64 r2 = pack2(rsqrt_approx(vx), rsqrt_approx(vy));
+      const u64 th2 = fmul2(pack2(vx, vy), r2);
+      if (QUANT) {
+        const u64 nd = fmul2(th2, k_neg), a2 = pack2(yv[i].x, yv[i].y);
+        u64 qq = fmul2(a2, r2);
+        qq = ffma2(ffma2(nd, qq, a2), r2, qq);
+        qq = ffma2(ffma2(nd, qq, a2), r2, qq);
+        float qx, qy;
+        unpack2(qq, qx, qy);
+        __stcs(&qv[32 * i], make_int2(__float2int_rn(qx), __float2int_rn(qy)));   // streaming: keep y in L2, not q
+      }
+      if (THR) __stcs(reinterpret_cast<u64*>(&tv[32 * i]), th2);
+    } else {
+      float v[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c] = 0.f;
+#pragma unroll
+      for (int sl = 0; sl < 3; ++sl) {
+        if (m & (1u << sl)) {
+          const VF g = *reinterpret_cast<const VF*>(gp + sl * GS);
+          const float* ga = reinterpret_cast<const float*>(&g);
+          const float w = sl == 0 ? f4[i].x : (sl == 1 ? f4[i].y : f4[i].z);
+#pragma unroll
+          for (int c = 0; c < C; ++c) v[c] = fmaf(ga[c], w, v[c]);
+        }
+      }
+      const float* ya = reinterpret_cast<const float*>(&yv[i]);
+      VF thr_v;
+      VI q_v;
+      float* th = reinterpret_cast<float*>(&thr_v);
+      int32_t* qa = reinterpret_cast<int32_t*>(&q_v);
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float vc = fmaxf(eps_s2, v[c]);
+        const float rs = rsqrt_approx(vc);
+        th[c] = vc * rs;
+        if (QUANT) {
+          float qq = ya[c] * rs;
+          qq = fmaf(fmaf(-th[c], qq, ya[c]), rs, qq);
+          qq = fmaf(fmaf(-th[c], qq, ya[c]), rs, qq);
+          qa[c] = __float2int_rn(qq);
+        }
+      }
+      if (QUANT) __stcs(&qv[32 * i], q_v);
+      if (THR) __stcs(&tv[32 * i], thr_v);
+    }
+  }
+}
+
 template <int C, bool QUANT, int NFIX>
 __global__ void __launch_bounds__(kThreads, 3)
 pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_constant__ PaJobParams jp,
                    const float* __restrict__ y, const float* __restrict__ ton_in, float one_minus_drown, float thr_scale,
-                   float* __restrict__ thr_out, int32_t* __restrict__ q_out, int64_t frames_total, int64_t tiles) {
+                   float* __restrict__ thr_out, int32_t* __restrict__ q_out, int64_t frames_total, int64_t tiles,
+                   const int ablate) {
   using VF = typename Vec<C>::F;
   using VI = typename Vec<C>::I;
   constexpr int TI = kTI, TS = kTS, GS = kGS, PS = kPS;
@@ -255,13 +342,12 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   static_assert(FT % kWarps == 0, "tile shape");
   extern __shared__ __align__(16) float sm[];
   const Layout2 L = layout2(tb);
-  const int n = NFIX > 0 ? NFIX : tb.n, kc = n < tb.chunk_k ? n : tb.chunk_k;
+  const int n = NFIX > 0 ? NFIX : tb.n, kc = n < tb.mma_chunk_k ? n : tb.mma_chunk_k;
+  const int n_chunks = tb.mma_n_chunks;
   float2* s_powa = reinterpret_cast<float2*>(sm + L.powa);
   float2* s_powia = reinterpret_cast<float2*>(sm + L.powia);
-  float* T = sm + L.t;                          // [kc + 3][TS]: I[k][item]
-  float* G = sm + L.t;                          // [64][GS]
   float* P = sm + L.p;                          // [64][PS], column item ^ ((band & 3) << 3)
-  float* s_part = sm + L.part;                  // [2][4][kPartS]
+  float* s_part = sm + L.part;                  // [2][kWarps][TI]: per-warp partial tonality sums
   float* s_u = sm + L.uv;                       // per item: offset_log2 (1 - drown) tonality
   float* s_v = s_u + TI;                        //           offset_log2 (1 - drown) (9 tonality + 5.5) + log2 scale^2
   float* s_ton = s_v + TI;
@@ -291,153 +377,133 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     s_quiet[i] = tb.quiet[i] * scale2;
     s_lin[i] = tb.lin[i];
   }
-  for (int i = tid; i < tb.n_band_w4; i += kThreads) {
-    const float w = tb.band_w4[i];
+  for (int i = tid; i < tb.n_mma_w4; i += kThreads) {
+    const float w = tb.mma_w4[i];
     s_bw8[2 * i] = w;
     s_bw8[2 * i + 1] = w;
   }
   if (filt_smem)
     for (int i = tid; i < n; i += kThreads) s_filt4[i] = tb.filt4[i];
-  __syncthreads();
 
   const uint32_t sm_base = static_cast<uint32_t>(__cvta_generic_to_shared(sm));
-  const uint32_t t_lane = sm_base + static_cast<uint32_t>(L.t) * 4u + static_cast<uint32_t>(lane) * 8u;
+  const uint32_t t_base = sm_base + static_cast<uint32_t>(L.t) * 4u;
+  const uint32_t tbuf_bytes = static_cast<uint32_t>(L.tbuf) * 4u;
   const uint32_t w_base = sm_base + static_cast<uint32_t>(L.bw8) * 4u;
   const uint32_t p_base = sm_base + static_cast<uint32_t>(L.p) * 4u;
   const float eps = tb.eps;
   const float eps_s2 = eps * scale2;
   const float log2_s2 = 2.0f * log2f(scale);
+
+  // y[f0 .. f0 + FT)[kc0 .. kc0 + kcn) -> T[buffer][filter][item], asynchronously.  Warp w copies its ROWS frame rows,
+  // lanes run along the filters (coalesced reads); frame rows behind the end of the tensor re-read the last frame
+  // (their results are never stored).  The three rows behind the chunk are zeroed for the 4-filter steps.
+  auto load_chunk = [&](int64_t f0, int nf, int chunk, int buf) {
+    if (ablate & 32) return;
+    const int kc0 = chunk * tb.mma_chunk_k;
+    const int kcn = (n - kc0 < kc ? n - kc0 : kc);
+    float* tz = sm + L.t + buf * L.tbuf + kcn * TS;
+    for (int i = tid; i < 3 * TS; i += kThreads) tz[i] = 0.f;
+    const uint32_t dst = t_base + static_cast<uint32_t>(buf) * tbuf_bytes + static_cast<uint32_t>(lane) * (TS * 4u) +
+                         static_cast<uint32_t>(warp * ROWS * C) * 4u;
+    const float* src = y + ((f0 + warp * ROWS) * static_cast<int64_t>(n) + kc0 + lane) * C;
+    const size_t rs = static_cast<size_t>(n) * C;          // row stride in floats (an immediate when N is fixed)
+    if (nf == FT && kcn == 64) {                // whole tile, whole chunk: straight-line copies
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+        for (int kk = 0; kk < 64; kk += 32) {
+          if constexpr (C == 1) {
+            cp_async<4>(dst + r * 4 + kk * (TS * 4), src + r * rs + kk);
+          } else {
+#pragma unroll
+            for (int c2 = 0; c2 < C; c2 += 2)
+              cp_async<8>(dst + (r * C + c2) * 4 + kk * (TS * 4), src + r * rs + kk * C + c2);
+          }
+        }
+    } else {
+#pragma unroll 1
+      for (int r = 0; r < ROWS; ++r) {
+        const int fl = warp * ROWS + r;
+        const float* srow = src + (fl < nf ? r : nf - 1 - warp * ROWS) * static_cast<int64_t>(rs);
+        for (int kk = 0; kk + lane < kcn; kk += 32) {
+          if constexpr (C == 1) {
+            cp_async<4>(dst + r * 4 + kk * (TS * 4), srow + kk);
+          } else {
+#pragma unroll
+            for (int c2 = 0; c2 < C; c2 += 2) cp_async<8>(dst + (r * C + c2) * 4 + kk * (TS * 4), srow + kk * C + c2);
+          }
+        }
+      }
+    }
+    cp_async_commit();
+  };
+
   // tiles are walked from the END of the tensor: the producer of y (the forward MDCT) wrote its last ~100 MB into
   // L2 most recently, and the consumer of thr / q (the inverse MDCT) starts at the front, where this kernel ends
+  int par = 0;                                  // buffer of the chunk that is processed next
+  if (static_cast<int64_t>(blockIdx.x) < tiles) {
+    const int64_t f0 = (tiles - 1 - blockIdx.x) * FT;
+    load_chunk(f0, static_cast<int>(frames_total - f0 < FT ? frames_total - f0 : FT), 0, 0);
+  }
   for (int64_t tile_i = blockIdx.x; tile_i < tiles; tile_i += gridDim.x) {
     const int64_t tile = tiles - 1 - tile_i;
     const int64_t f0 = tile * FT;
     const int nf = static_cast<int>(frames_total - f0 < FT ? frames_total - f0 : FT);
 
-    float t_sum[ROWS][C], t_log[ROWS][C];       // tonality sums of this warp's frame rows (psychoacoustic.py:113-116)
-#pragma unroll
-    for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-      for (int c = 0; c < C; ++c) t_sum[r][c] = t_log[r][c] = 0.f;
-
-    for (int chunk = 0; chunk < tb.n_chunks; ++chunk) {
-      const int kc0 = chunk * tb.chunk_k;
+    u64 ton_i2 = 0ull, ton_l2 = 0ull;           // tonality sums (psychoacoustic.py:113-116) of the item pair of this lane
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      const int kc0 = chunk * tb.mma_chunk_k;
       const int kcn = (n - kc0 < kc ? n - kc0 : kc);          // filters in this chunk
-      // ---- A1: I = y^2, transposed; tonality sums                         (psychoacoustic.py:113, :312)
-      // frame rows behind the end of the tensor re-read the last frame: their results are never stored
-      if (kcn < kc || chunk == 0)                              // zero rows behind a short (or the first) chunk
-        for (int i = tid; i < 3 * TS; i += kThreads) T[kcn * TS + i] = 0.f;
-      if ((kcn & 127) == 0) {
-        for (int kb = 0; kb < kcn; kb += 128) {         // whole 128-filter pieces: all loads first
-          VF v[ROWS][4];
-#pragma unroll
-          for (int r = 0; r < ROWS; ++r) {
-            const int fl = min(warp * ROWS + r, nf - 1);
-            const VF* row = reinterpret_cast<const VF*>(y) + ((f0 + fl) * static_cast<int64_t>(n) + kc0 + kb + lane);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) v[r][u] = __ldg(row + u * 32);
-          }
-#pragma unroll
-          for (int r = 0; r < ROWS; ++r) {
-            float* tp = T + (kb + lane) * TS + (warp * ROWS + r) * C;
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float* a = reinterpret_cast<const float*>(&v[r][u]);
-              if constexpr (C == 2) {      // both channels in one packed multiply / add (same IEEE results per half)
-                const u64 a2 = pack2(a[0], a[1]);
-                const u64 in2 = fmul2(a2, a2);
-                float ix, iy;
-                unpack2(in2, ix, iy);
-                *reinterpret_cast<u64*>(tp + u * 32 * TS) = in2;
-                u64 s2 = fadd2(pack2(t_sum[r][0], t_sum[r][1]), in2);
-                unpack2(s2, t_sum[r][0], t_sum[r][1]);
-                u64 l2 = fadd2(pack2(t_log[r][0], t_log[r][1]), pack2(lg2_approx(fmaxf(eps, ix)), lg2_approx(fmaxf(eps, iy))));
-                unpack2(l2, t_log[r][0], t_log[r][1]);
-              } else {
-                float in[C];
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                  in[c] = a[c] * a[c];
-                  t_sum[r][c] += in[c];
-                  t_log[r][c] += lg2_approx(fmaxf(eps, in[c]));
-                }
-                if constexpr (C == 4) {
-                  *reinterpret_cast<float2*>(tp + u * 32 * TS) = make_float2(in[0], in[1]);
-                  *reinterpret_cast<float2*>(tp + u * 32 * TS + 2) = make_float2(in[2], in[3]);
-                } else {
-                  tp[u * 32 * TS] = in[0];
-                }
-              }
-            }
-          }
-        }
-      } else {
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-          const int fl = warp * ROWS + r;
-          const VF* row = reinterpret_cast<const VF*>(y) + ((f0 + min(fl, nf - 1)) * static_cast<int64_t>(n) + kc0);
-          float* tcol = T + fl * C;
-          for (int kb = 0; kb < kcn; kb += 32) {
-            const int k = kb + lane;
-            if (k < kcn) {
-              const VF v = __ldg(row + k);
-              const float* a = reinterpret_cast<const float*>(&v);
-#pragma unroll
-              for (int c = 0; c < C; ++c) {
-                const float in = a[c] * a[c];
-                tcol[k * TS + c] = in;
-                t_sum[r][c] += in;
-                t_log[r][c] += lg2_approx(fmaxf(eps, in));
-              }
-            }
-          }
-        }
+      cp_async_wait_all();
+      __syncthreads();                          // the chunk has landed; the other buffer (and G in it) is free
+      if (chunk + 1 < n_chunks) {
+        load_chunk(f0, nf, chunk + 1, par ^ 1);
+      } else if (tile_i + gridDim.x < tiles) {
+        const int64_t nf0 = (tile - gridDim.x) * FT;
+        load_chunk(nf0, static_cast<int>(frames_total - nf0 < FT ? frames_total - nf0 : FT), 0, par ^ 1);
       }
-      const bool last_chunk = chunk == tb.n_chunks - 1;
-      if (last_chunk && ton_in == nullptr) {
-        // fold the 32 lane partials of every row to 4 and park them for the lane <-> item pass
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-          for (int c = 0; c < C; ++c) {
-            float a = t_sum[r][c], b = t_log[r][c];
-#pragma unroll
-            for (int o = 16; o >= 4; o >>= 1) {
-              a += __shfl_xor_sync(0xffffffffu, a, o);
-              b += __shfl_xor_sync(0xffffffffu, b, o);
-            }
-            if (lane < 4) {
-              const int item = (warp * ROWS + r) * C + c;
-              s_part[lane * kPartS + item] = a;
-              s_part[(4 + lane) * kPartS + item] = b;
-            }
-          }
-      }
-      __syncthreads();
+      const uint32_t t_lane = t_base + static_cast<uint32_t>(par) * tbuf_bytes + static_cast<uint32_t>(lane) * 8u;
 
-      // ---- per-item constants of the masking offset (psychoacoustic.py:185-191), once per tile
-      if (last_chunk && warp < TI / 32) {
-        const int it = warp * 32 + lane;
-        float ton;
-        if (ton_in == nullptr) {                         // tonality of the item (psychoacoustic.py:113-118)
-          const float* sp = s_part + it;
-          const float s_i = (sp[0] + sp[kPartS]) + (sp[2 * kPartS] + sp[3 * kPartS]);
-          const float s_l = (sp[4 * kPartS] + sp[5 * kPartS]) + (sp[6 * kPartS] + sp[7 * kPartS]);
-          ton = tonality_from_log2_sums(s_i, s_l, n, eps);
-        } else {
-          const int64_t item = f0 * C + it;
-          ton = item < frames_total * C ? __ldg(ton_in + item) : 0.f;
+      // ---- A1: tonality sums over this warp's share of the filters: sum I and sum log2 max(eps, I)   (:113, :312)
+      // two filters per logarithm: log2 a + log2 b = log2(a b), a b >= eps^2 (finite for |y| < 1e9)
+      if (ton_in == nullptr && !(ablate & 1)) {
+        auto lds_t = [&](int k) {
+          u64 a2;
+          asm volatile("ld.shared.b64 %0, [%1];" : "=l"(a2) : "r"(t_lane + static_cast<uint32_t>(k) * (TS * 4u)));
+          return a2;
+        };
+        auto clamp2 = [&](u64 in2) {
+          float ix, iy;
+          unpack2(in2, ix, iy);
+          return pack2(fmaxf(eps, ix), fmaxf(eps, iy));
+        };
+        int k = warp;
+        if (kcn == 64) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const u64 a2 = lds_t(warp + 16 * u), b2 = lds_t(warp + 16 * u + 8);
+            const u64 ia = fmul2(a2, a2), ib = fmul2(b2, b2);
+            ton_i2 = fadd2(ton_i2, fadd2(ia, ib));
+            float px, py;
+            unpack2(fmul2(clamp2(ia), clamp2(ib)), px, py);
+            ton_l2 = fadd2(ton_l2, pack2(lg2_approx(px), lg2_approx(py)));
+          }
+          k = kcn;
         }
-        const float ko = tb.offset_log2 * one_minus_drown;
-        s_u[it] = ko * ton;
-        s_v[it] = fmaf(ko, fmaf(9.f, ton, 5.5f), log2_s2);
-        s_ton[it] = ton;
+        for (; k < kcn; k += kWarps) {
+          const u64 a2 = lds_t(k);
+          const u64 in2 = fmul2(a2, a2);
+          float ix, iy;
+          unpack2(clamp2(in2), ix, iy);
+          ton_i2 = fadd2(ton_i2, in2);
+          ton_l2 = fadd2(ton_l2, pack2(lg2_approx(ix), lg2_approx(iy)));
+        }
       }
 
       // ---- A2: band energies of this chunk; P = max(eps, I_bark)^alpha when a band is complete  (:204-206, :313)
-      // lane l owns the item pair (2l, 2l + 1) as packed fp32: one LDS.64 and one FFMA2 per filter for two items
+      // lane l owns the item pair (2l, 2l + 1) as packed fp32: one LDS.64, a square and one FFMA2 per filter
       {
-        const int j0 = jp.start[chunk * 9 + warp_u], j1 = jp.start[chunk * 9 + warp_u + 1];
+        const int j0 = jp.start[chunk * 9 + warp_u], j1 = (ablate & 2) ? j0 : jp.start[chunk * 9 + warp_u + 1];
 #pragma unroll 1
         for (int j = j0; j < j1; ++j) {
           const int4 jb = jp.job[j];           // { T byte offset, weight byte offset, steps, P byte offset | flags << 16 }
@@ -452,14 +518,17 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
             lds_2b64<16>(wp, w2, w3);
             lds_2b64<32>(wp, w4, w5);
             lds_2b64<48>(wp, w6, w7);
-            a0 = ffma2(lds_b64<0>(tp), w0, a0);
-            a1 = ffma2(lds_b64<4 * TS * 4>(tp), w4, a1);
-            a0 = ffma2(lds_b64<1 * TS * 4>(tp), w1, a0);
-            a1 = ffma2(lds_b64<5 * TS * 4>(tp), w5, a1);
-            a0 = ffma2(lds_b64<2 * TS * 4>(tp), w2, a0);
-            a1 = ffma2(lds_b64<6 * TS * 4>(tp), w6, a1);
-            a0 = ffma2(lds_b64<3 * TS * 4>(tp), w3, a0);
-            a1 = ffma2(lds_b64<7 * TS * 4>(tp), w7, a1);
+            const u64 y0 = lds_b64<0>(tp), y4 = lds_b64<4 * TS * 4>(tp), y1 = lds_b64<1 * TS * 4>(tp);
+            const u64 y5 = lds_b64<5 * TS * 4>(tp), y2 = lds_b64<2 * TS * 4>(tp), y6 = lds_b64<6 * TS * 4>(tp);
+            const u64 y3 = lds_b64<3 * TS * 4>(tp), y7 = lds_b64<7 * TS * 4>(tp);
+            a0 = ffma2(fmul2(y0, y0), w0, a0);
+            a1 = ffma2(fmul2(y4, y4), w4, a1);
+            a0 = ffma2(fmul2(y1, y1), w1, a0);
+            a1 = ffma2(fmul2(y5, y5), w5, a1);
+            a0 = ffma2(fmul2(y2, y2), w2, a0);
+            a1 = ffma2(fmul2(y6, y6), w6, a1);
+            a0 = ffma2(fmul2(y3, y3), w3, a0);
+            a1 = ffma2(fmul2(y7, y7), w7, a1);
             tp += 8 * TS * 4;
             wp += 64;
           }
@@ -467,10 +536,12 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
             u64 w0, w1, w2, w3;
             lds_2b64<0>(wp, w0, w1);
             lds_2b64<16>(wp, w2, w3);
-            a0 = ffma2(lds_b64<0>(tp), w0, a0);
-            a1 = ffma2(lds_b64<1 * TS * 4>(tp), w1, a1);
-            a0 = ffma2(lds_b64<2 * TS * 4>(tp), w2, a0);
-            a1 = ffma2(lds_b64<3 * TS * 4>(tp), w3, a1);
+            const u64 y0 = lds_b64<0>(tp), y1 = lds_b64<1 * TS * 4>(tp), y2 = lds_b64<2 * TS * 4>(tp);
+            const u64 y3 = lds_b64<3 * TS * 4>(tp);
+            a0 = ffma2(fmul2(y0, y0), w0, a0);
+            a1 = ffma2(fmul2(y1, y1), w1, a1);
+            a0 = ffma2(fmul2(y2, y2), w2, a0);
+            a1 = ffma2(fmul2(y3, y3), w3, a1);
           }
           u64 acc2 = fadd2(a0, a1);
           const uint32_t pp = p_base + ((static_cast<uint32_t>(jb.w) & 0xffffu) ^ (static_cast<uint32_t>(lane) << 3));
@@ -483,7 +554,35 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
           sts_b64(pp, acc2);
         }
       }
-      __syncthreads();
+      par ^= 1;
+    }
+    float* G = sm + L.t + (par ^ 1) * L.tbuf;   // [64][GS] in the buffer of the last chunk; `par` is being filled
+    if (ton_in == nullptr) {
+      *reinterpret_cast<u64*>(s_part + warp * TI + 2 * lane) = ton_i2;
+      *reinterpret_cast<u64*>(s_part + (kWarps + warp) * TI + 2 * lane) = ton_l2;
+    }
+    __syncthreads();                            // P and the tonality partials are complete
+
+    // ---- per-item constants of the masking offset (psychoacoustic.py:185-191), once per tile
+    if (warp < TI / 32) {
+      const int it = warp * 32 + lane;
+      float ton;
+      if (ton_in == nullptr) {                         // tonality of the item (psychoacoustic.py:113-118)
+        float s_i = 0.f, s_l = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+          s_i += s_part[w * TI + it];
+          s_l += s_part[(kWarps + w) * TI + it];
+        }
+        ton = tonality_from_log2_sums(s_i, s_l, n, eps);
+      } else {
+        const int64_t item = f0 * C + it;
+        ton = item < frames_total * C ? __ldg(ton_in + item) : 0.f;
+      }
+      const float ko = tb.offset_log2 * one_minus_drown;
+      s_u[it] = ko * ton;
+      s_v[it] = fmaf(ko, fmaf(9.f, ton, 5.5f), log2_s2);
+      s_ton[it] = ton;
     }
 
     // ---- B: spreading on the tensor cores                                 (psychoacoustic.py:195-206)
@@ -517,6 +616,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       }
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
+        if (ablate & 4) break;
         if (ks > 0) {
 #pragma unroll
           for (int nt = 3; nt > 0; --nt) {
@@ -544,9 +644,11 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
         }
       }
 
+      __syncthreads();                          // the per-item constants are visible; P is free
       // masking offset, non-linear superposition, quiet threshold            (psychoacoustic.py:185-208, :144)
       const int ma = m0 + g, mb = m0 + g + 8;
-      if (!tb.clamp_needed) {
+      if (ablate & 8) {
+      } else if (!tb.clamp_needed) {
         const float ua = s_u[ma], va = s_v[ma], ub = s_u[mb], vb = s_v[mb];
         const float inva = tb.inv_alpha;
 #pragma unroll
@@ -586,25 +688,55 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     __syncthreads();
 
     // ---- D: back to the filter bands, amplitude, optional quantiser      (:330-331; quantiser: SURVEY 8a row Q)
+    // units of KI x 32 filters: the unit's filter-table entries stay in registers for all rows of the warp; a row
+    // of a unit is KI x 32 x C contiguous floats of thr and of q (long DRAM bursts)
     {
       const bool thr = thr_out != nullptr;
+      constexpr int KI = C == 4 ? 4 : 8;
+      const int rows_live = (ablate & 16) ? 0 : min(ROWS, nf - warp * ROWS);
+      if (n % (32 * KI) == 0) {
+        const int64_t off0 = ((f0 + warp * ROWS) * static_cast<int64_t>(n) + lane) * C;   // rows of a warp are contiguous
+        const size_t rs = static_cast<size_t>(n) * C;
 #pragma unroll 1
-      for (int r = 0; r < ROWS; ++r) {
-        const int fl = warp * ROWS + r;
-        if (fl >= nf) break;
-        const int64_t off = (f0 + fl) * static_cast<int64_t>(n) * C;
-        const float* gr = G + fl * C;
+        for (int k0 = 0; k0 < n; k0 += 32 * KI) {
+          float4 f4[KI];
+#pragma unroll
+          for (int i = 0; i < KI; ++i)
+            f4[i] = filt_smem ? s_filt4[k0 + 32 * i + lane] : __ldg(tb.filt4 + k0 + 32 * i + lane);
+          unsigned masks = 0;
+#pragma unroll
+          for (int i = 0; i < KI; ++i) masks |= static_cast<unsigned>(tb.filt_mask[k0 / 32 + i]) << (3 * i);
+#pragma unroll 1
+          for (int r = 0; r < rows_live; ++r) {
+            const int64_t off = off0 + r * rs + static_cast<int64_t>(k0) * C;
+            VF yv[KI];
+            if (QUANT) {
+#pragma unroll
+              for (int i = 0; i < KI; ++i) yv[i] = __ldg(reinterpret_cast<const VF*>(y + off) + 32 * i);
+            }
+            const float* gr = G + (warp * ROWS + r) * C;
+            if (thr) phase_d_unit<C, QUANT, true, KI>(f4, masks, yv, thr_out + off, q_out + off, gr, eps_s2);
+            else     phase_d_unit<C, QUANT, false, KI>(f4, masks, yv, thr_out + off, q_out + off, gr, eps_s2);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int r = 0; r < rows_live; ++r) {
+          const int fl = warp * ROWS + r;
+          const int64_t off = (f0 + fl) * static_cast<int64_t>(n) * C;
+          const float* gr = G + fl * C;
 #define AC_PHASE_D(THR_, FS_) \
   phase_d_row<C, QUANT, THR_, FS_, NFIX>(FS_ ? s_filt4 : tb.filt4, n, lane, y + off, thr_out + off, q_out + off, gr, eps_s2)
-        if (filt_smem) {
-          if (thr) AC_PHASE_D(true, true); else AC_PHASE_D(false, true);
-        } else {
-          if (thr) AC_PHASE_D(true, false); else AC_PHASE_D(false, false);
-        }
+          if (filt_smem) {
+            if (thr) AC_PHASE_D(true, true); else AC_PHASE_D(false, true);
+          } else {
+            if (thr) AC_PHASE_D(true, false); else AC_PHASE_D(false, false);
+          }
 #undef AC_PHASE_D
+        }
       }
     }
-    __syncthreads();       // G (aliasing T) and P are rewritten by the next tile
+    // no barrier here: G's buffer and P are next written behind the first barrier of the next tile
   }
 }
 
@@ -629,12 +761,16 @@ cudaError_t launch_mma_tile_n(const PaDeviceTables& tb, const float* y, const fl
   const int64_t tiles = (frames + FT - 1) / FT;
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
   per_sm = per_sm > 3 ? 3 : (per_sm < 1 ? 1 : per_sm);
+  if (const char* e = std::getenv("AC_PA_CTAS")) per_sm = std::max(1, std::min(per_sm, std::atoi(e)));   // experiments
   const int64_t cap = static_cast<int64_t>(mma_sm_count()) * per_sm;
   const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+  int ablate = 0;
+  if (const char* e = std::getenv("AC_PA_ABLATE")) ablate = std::atoi(e);   // experiments: skip phases (wrong results)
   auto kernel = pa_mma_tile_kernel<C, QUANT, NFIX>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
-  kernel<<<grid, kThreads, smem, stream>>>(tb, *tb.jobs_host, y, ton_in, omd, thr_scale, thr_out, q_out, frames, tiles);
+  kernel<<<grid, kThreads, smem, stream>>>(tb, *tb.jobs_host, y, ton_in, omd, thr_scale, thr_out, q_out, frames, tiles,
+                                           ablate);
   count_launch();
   return cudaGetLastError();
 }
