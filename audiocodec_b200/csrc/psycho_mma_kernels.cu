@@ -252,12 +252,12 @@ __device__ __forceinline__ void phase_d_row(const float4* __restrict__ filt4, co
   }
 }
 
-// The same for KI x 32 consecutive filters of a row with the filter-table entries f4[i] (filter k0 + 32 i + lane) held
-// in registers by the caller for all rows of the warp, and the y values yv[i] loaded by the caller.  masks: three bits
+// The same for KI x 32 consecutive filters of a row (filt4 points at this lane's first entry) with the y values yv[i]
+// (filter k0 + 32 i + lane) loaded ahead of time by the caller.  masks: three bits
 // per 32-filter group, bit s set when any filter of the group has a non-zero weight for band slot s - the shared-memory
 // loads of unused slots are skipped (warp-uniform predicates; a skipped term is an exact + 0).
-template <int C, bool QUANT, bool THR, int KI>
-__device__ __forceinline__ void phase_d_unit(const float4 (&f4)[KI], const unsigned masks,
+template <int C, bool QUANT, bool THR, bool FILT_SMEM, int KI>
+__device__ __forceinline__ void phase_d_unit(const float4* __restrict__ filt4, const unsigned masks,
                                              const typename Vec<C>::F (&yv)[KI], float* __restrict__ trow,
                                              int32_t* __restrict__ qrow, const float* gr, const float eps_s2) {
   using VF = typename Vec<C>::F;
@@ -268,13 +268,14 @@ __device__ __forceinline__ void phase_d_unit(const float4 (&f4)[KI], const unsig
   const u64 k_neg = pack2(-1.f, -1.f);
 #pragma unroll
   for (int i = 0; i < KI; ++i) {
-    const float* gp = gr + __float_as_int(f4[i].w) * GS;
+    const float4 f4i = FILT_SMEM ? filt4[32 * i] : __ldg(filt4 + 32 * i);
+    const float* gp = gr + __float_as_int(f4i.w) * GS;
     const unsigned m = masks >> (3 * i);
     if constexpr (C == 2) {
       u64 v2 = 0ull;
-      if (m & 1u) v2 = fmul2(*reinterpret_cast<const u64*>(gp), pack2(f4[i].x, f4[i].x));
-      if (m & 2u) v2 = ffma2(*reinterpret_cast<const u64*>(gp + GS), pack2(f4[i].y, f4[i].y), v2);
-      if (m & 4u) v2 = ffma2(*reinterpret_cast<const u64*>(gp + 2 * GS), pack2(f4[i].z, f4[i].z), v2);
+      if (m & 1u) v2 = fmul2(*reinterpret_cast<const u64*>(gp), pack2(f4i.x, f4i.x));
+      if (m & 2u) v2 = ffma2(*reinterpret_cast<const u64*>(gp + GS), pack2(f4i.y, f4i.y), v2);
+      if (m & 4u) v2 = ffma2(*reinterpret_cast<const u64*>(gp + 2 * GS), pack2(f4i.z, f4i.z), v2);
       float vx, vy;
       unpack2(v2, vx, vy);
       vx = fmaxf(eps_s2, vx);
@@ -300,7 +301,7 @@ __device__ __forceinline__ void phase_d_unit(const float4 (&f4)[KI], const unsig
         if (m & (1u << sl)) {
           const VF g = *reinterpret_cast<const VF*>(gp + sl * GS);
           const float* ga = reinterpret_cast<const float*>(&g);
-          const float w = sl == 0 ? f4[i].x : (sl == 1 ? f4[i].y : f4[i].z);
+          const float w = sl == 0 ? f4i.x : (sl == 1 ? f4i.y : f4i.z);
 #pragma unroll
           for (int c = 0; c < C; ++c) v[c] = fmaf(ga[c], w, v[c]);
         }
@@ -695,29 +696,40 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       constexpr int KI = C == 4 ? 4 : 8;
       const int rows_live = (ablate & 16) ? 0 : min(ROWS, nf - warp * ROWS);
       if (n % (32 * KI) == 0) {
-        const int64_t off0 = ((f0 + warp * ROWS) * static_cast<int64_t>(n) + lane) * C;   // rows of a warp are contiguous
-        const size_t rs = static_cast<size_t>(n) * C;
-#pragma unroll 1
-        for (int k0 = 0; k0 < n; k0 += 32 * KI) {
-          float4 f4[KI];
+        // the rows of a warp are contiguous in memory: its units are one flat sequence; the y values of unit u + 1
+        // are loaded (an L2 hit) before unit u is computed
+        const int upr = n / (32 * KI);          // units per row
+        const int units = rows_live > 0 ? rows_live * upr : 0;
+        const int64_t off0 = ((f0 + warp * ROWS) * static_cast<int64_t>(n) + lane) * C;
+        const VF* yp = reinterpret_cast<const VF*>(y + off0);
+        VF ynext[KI];
+        if (QUANT && units > 0) {
 #pragma unroll
-          for (int i = 0; i < KI; ++i)
-            f4[i] = filt_smem ? s_filt4[k0 + 32 * i + lane] : __ldg(tb.filt4 + k0 + 32 * i + lane);
+          for (int i = 0; i < KI; ++i) ynext[i] = __ldg(yp + 32 * i);
+        }
+#pragma unroll 1
+        for (int u = 0; u < units; ++u) {
+          VF ycur[KI];
+#pragma unroll
+          for (int i = 0; i < KI; ++i) ycur[i] = ynext[i];
+          if (QUANT && u + 1 < units) {
+#pragma unroll
+            for (int i = 0; i < KI; ++i) ynext[i] = __ldg(yp + (u + 1) * (32 * KI) + 32 * i);
+          }
+          const int r = u / upr, k0 = (u - r * upr) * (32 * KI);
           unsigned masks = 0;
 #pragma unroll
           for (int i = 0; i < KI; ++i) masks |= static_cast<unsigned>(tb.filt_mask[k0 / 32 + i]) << (3 * i);
-#pragma unroll 1
-          for (int r = 0; r < rows_live; ++r) {
-            const int64_t off = off0 + r * rs + static_cast<int64_t>(k0) * C;
-            VF yv[KI];
-            if (QUANT) {
-#pragma unroll
-              for (int i = 0; i < KI; ++i) yv[i] = __ldg(reinterpret_cast<const VF*>(y + off) + 32 * i);
-            }
-            const float* gr = G + (warp * ROWS + r) * C;
-            if (thr) phase_d_unit<C, QUANT, true, KI>(f4, masks, yv, thr_out + off, q_out + off, gr, eps_s2);
-            else     phase_d_unit<C, QUANT, false, KI>(f4, masks, yv, thr_out + off, q_out + off, gr, eps_s2);
+          const int64_t off = off0 + static_cast<int64_t>(u) * (32 * KI * C);
+          const float* gr = G + (warp * ROWS + r) * C;
+#define AC_PHASE_D(THR_, FS_) \
+  phase_d_unit<C, QUANT, THR_, FS_, KI>((FS_ ? s_filt4 : tb.filt4) + k0 + lane, masks, ycur, thr_out + off, q_out + off, gr, eps_s2)
+          if (filt_smem) {
+            if (thr) AC_PHASE_D(true, true); else AC_PHASE_D(false, true);
+          } else {
+            if (thr) AC_PHASE_D(true, false); else AC_PHASE_D(false, false);
           }
+#undef AC_PHASE_D
         }
       } else {
 #pragma unroll 1
