@@ -272,10 +272,18 @@ __device__ __forceinline__ void phase_d_unit(const float4* __restrict__ filt4, c
     const float* gp = gr + __float_as_int(f4i.w) * GS;
     const unsigned m = masks >> (3 * i);
     if constexpr (C == 2) {
-      u64 v2 = 0ull;
-      if (m & 1u) v2 = fmul2(*reinterpret_cast<const u64*>(gp), pack2(f4i.x, f4i.x));
-      if (m & 2u) v2 = ffma2(*reinterpret_cast<const u64*>(gp + GS), pack2(f4i.y, f4i.y), v2);
-      if (m & 4u) v2 = ffma2(*reinterpret_cast<const u64*>(gp + 2 * GS), pack2(f4i.z, f4i.z), v2);
+      u64 v2;                                    // warp-uniform branch on the slot pattern of the 32-filter group
+      if ((m & 7u) == 3u) {
+        v2 = ffma2(*reinterpret_cast<const u64*>(gp + GS), pack2(f4i.y, f4i.y),
+                   fmul2(*reinterpret_cast<const u64*>(gp), pack2(f4i.x, f4i.x)));
+      } else if ((m & 7u) == 6u) {
+        v2 = ffma2(*reinterpret_cast<const u64*>(gp + 2 * GS), pack2(f4i.z, f4i.z),
+                   fmul2(*reinterpret_cast<const u64*>(gp + GS), pack2(f4i.y, f4i.y)));
+      } else {
+        v2 = ffma2(*reinterpret_cast<const u64*>(gp + 2 * GS), pack2(f4i.z, f4i.z),
+                   ffma2(*reinterpret_cast<const u64*>(gp + GS), pack2(f4i.y, f4i.y),
+                         fmul2(*reinterpret_cast<const u64*>(gp), pack2(f4i.x, f4i.x))));
+      }
       float vx, vy;
       unpack2(v2, vx, vy);
       vx = fmaxf(eps_s2, vx);
@@ -777,7 +785,9 @@ cudaError_t launch_mma_tile_n(const PaDeviceTables& tb, const float* y, const fl
   const int64_t cap = static_cast<int64_t>(mma_sm_count()) * per_sm;
   const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
   int ablate = 0;
-  if (const char* e = std::getenv("AC_PA_ABLATE")) ablate = std::atoi(e);   // experiments: skip phases (wrong results)
+  // experiments (profiles/README.md, ablation table): bit 0 skips the tonality pass, 1 the band sums, 2 the MMA loop,
+  // 3 its epilogue, 4 phase D, 5 the asynchronous copies of y - the results are then wrong, only the time is of interest
+  if (const char* e = std::getenv("AC_PA_ABLATE")) ablate = std::atoi(e);
   auto kernel = pa_mma_tile_kernel<C, QUANT, NFIX>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;

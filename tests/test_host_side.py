@@ -118,3 +118,15 @@ def test_product_does_not_import_oracle():
       if name.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
         text = open(os.path.join(dirpath, name)).read()
         assert "oracle" not in text.replace("the oracle", "").replace("The oracle", ""), name
+
+
+def test_pa_mma_index_maps_emulation():
+  """NumPy emulation of the tensor-core tile kernel's fragment addressing (tools/emulate_pa_mma.py): the swizzled P
+  layout, the mma.m16n8k8 fragments and the rotating Toeplitz B fragments compute P^T S, bank-conflict free."""
+  import importlib.util
+  import pathlib
+  path = pathlib.Path(__file__).resolve().parents[1] / "tools" / "emulate_pa_mma.py"
+  spec = importlib.util.spec_from_file_location("emulate_pa_mma", path)
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  mod.main()

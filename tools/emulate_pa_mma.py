@@ -6,7 +6,7 @@ the shared-memory accesses involved are bank-conflict free.
 """
 import numpy as np
 
-TI, GS, NB = 32, 36, 64
+TI, GS, NB = 64, 68, 64        # items per tile, row stride of G, bark bands (psycho_mma_kernels.cu)
 
 
 def mma_m16n8k8(acc, a, b):
@@ -35,16 +35,18 @@ def main():
   rng = np.random.default_rng(0)
   p_true = rng.random((TI, NB)) + 0.1          # [item][band]
   sf = rng.random(128) + 0.1
-  # A2 store: P[band * TI + (item ^ ((band & 3) << 3))], lane <-> item
+  # A2 store: lane l owns the item pair (2l, 2l + 1): one 64-bit store at P[band * TI + ((2l) ^ ((band & 3) << 3))]
   P = np.zeros(NB * TI)
   for band in range(NB):
-    addrs = [band * TI + (lane ^ ((band & 3) << 3)) for lane in range(32)]
-    assert banks_ok(addrs)
+    addrs = [band * TI + ((2 * lane) ^ ((band & 3) << 3)) for lane in range(32)]
+    for half in (addrs[:16], addrs[16:]):          # a 64-bit access is served per half-warp
+      assert banks_ok(half) and banks_ok([a + 1 for a in half])
     for lane in range(32):
-      P[addrs[lane]] = p_true[lane, band]
+      P[addrs[lane]] = p_true[2 * lane, band]
+      P[addrs[lane] + 1] = p_true[2 * lane + 1, band]
   G = np.full(NB * GS, np.nan)
-  for warp in range(4):
-    m0, nq = (warp & 1) * 16, warp >> 1
+  for warp in range(8):
+    m0, nq = (warp & 3) * 16, warp >> 2
     acc = np.zeros((4, 32, 4))
     b = [None] * 4
     lanes = range(32)
