@@ -256,3 +256,44 @@ def test_mma_tile_kernel_against_other_kernels(sr, n, c, b, m, monkeypatch):
     diff = np.abs(out["mma"][0].astype(np.int64) - out[other][0])
     assert diff.max() <= 1 and np.mean(diff == 0) >= 0.999
   np.testing.assert_allclose(out["mma"][1], 1.5 * out["mma"][2], rtol=2e-6)
+
+
+def test_unaligned_views_take_the_generic_kernel():
+  """A 4-byte-aligned view (odd float offset into a larger buffer) must not reach the vectorised tile kernels."""
+  n, c = 256, 2
+  pa = audiocodec_b200.PsychoacousticModel(44100, n)
+  rng = np.random.default_rng(5)
+  y = cuda(rng.standard_normal((2, 9, n, c)).astype(np.float32))
+  buf = torch.empty(y.numel() + 1, device="cuda")
+  view = buf[1:].view(y.shape)
+  view.copy_(y)
+  q_ref, step_ref = pa.encode(y)
+  q, step = pa.encode(view)
+  np.testing.assert_allclose(step.cpu().numpy(), step_ref.cpu().numpy(), rtol=5e-6)
+  assert (q - q_ref).abs().max().item() <= 1
+
+
+def test_non_finite_amplitudes_stay_local():
+  """inf / NaN coefficients poison their own (frame, channel) item only and never fault (exponent-table lookups stay
+  inside the shared-memory allocation whatever the bit pattern)."""
+  n, c = 256, 2
+  pa = audiocodec_b200.PsychoacousticModel(44100, n)
+  rng = np.random.default_rng(11)
+  y = rng.standard_normal((2, 70, n, c)).astype(np.float32)
+  bad = y.copy()
+  bad[0, 3, 17, 0] = np.inf
+  bad[1, 40, 200, 1] = np.nan
+  bad[1, 41, 5, 0] = -np.inf
+  q_ref, step_ref = pa.encode(cuda(y))
+  q, step = pa.encode(cuda(bad))
+  torch.cuda.synchronize()
+  keep = np.ones((2, 70, c), dtype=bool)
+  keep[0, 3, 0] = keep[1, 40, 1] = keep[1, 41, 0] = False
+  step, step_ref = step.cpu().numpy(), step_ref.cpu().numpy()
+  q, q_ref = q.cpu().numpy(), q_ref.cpu().numpy()
+  for b in range(2):
+    for f in range(70):
+      for ch in range(c):
+        if keep[b, f, ch]:
+          assert np.array_equal(step[b, f, :, ch], step_ref[b, f, :, ch])
+          assert np.array_equal(q[b, f, :, ch], q_ref[b, f, :, ch])
