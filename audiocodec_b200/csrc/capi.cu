@@ -696,7 +696,30 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
     if (err != cudaSuccess) return cuda_fail(err, "allocating the device staging of the batch");
     p->capacity_clips = batches;
   }
-  const size_t n_chunks = static_cast<size_t>((batches + p->chunk_clips - 1) / p->chunk_clips);
+  // chunk schedule: small chunks at both ends (1, 1, 2, 4, ... clips up to chunk_clips and down again) keep the
+  // fill (first H2D + kernels before the first D2H can start) and the drain (last kernels + D2H) of the pipeline
+  // short; the middle runs at the full chunk size
+  std::vector<int64_t> chunk_of;
+  {
+    std::vector<int64_t> head, tail;
+    int64_t left = batches, next = 1;
+    bool first = true;
+    while (left > 0) {
+      int64_t h = std::min(std::min(next, p->chunk_clips), left);
+      head.push_back(h);
+      left -= h;
+      if (left > 0) {
+        int64_t t = std::min(std::min(next, p->chunk_clips), left);
+        tail.push_back(t);
+        left -= t;
+      }
+      if (!first) next *= 2;
+      first = false;
+    }
+    chunk_of = head;
+    chunk_of.insert(chunk_of.end(), tail.rbegin(), tail.rend());
+  }
+  const size_t n_chunks = chunk_of.size();
   while (p->x_ready.size() < n_chunks && err == cudaSuccess) {
     cudaEvent_t a = nullptr, b = nullptr;
     ok(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -714,15 +737,15 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
   if (stats != nullptr) ok(cudaMemsetAsync(p->stats_dev, 0, 3 * sizeof(unsigned long long), p->run));
   // all the H2D copies first: nothing on that stream depends on the kernels
   size_t k = 0;
-  for (int64_t i = 0; i < batches && err == cudaSuccess; i += p->chunk_clips, ++k) {
-    const int64_t cb = std::min(p->chunk_clips, batches - i);
+  for (int64_t i = 0; k < n_chunks && err == cudaSuccess; i += chunk_of[k], ++k) {
+    const int64_t cb = chunk_of[k];
     if (in_clip > 0)
       ok(cudaMemcpyAsync(p->x_all + i * in_clip, x_host + i * in_clip, cb * in_clip * sizeof(float), cudaMemcpyHostToDevice, p->h2d));
     ok(cudaEventRecord(p->x_ready[k], p->h2d));
   }
   k = 0;
-  for (int64_t i = 0; i < batches && err == cudaSuccess; i += p->chunk_clips, ++k) {
-    const int64_t cb = std::min(p->chunk_clips, batches - i);
+  for (int64_t i = 0; k < n_chunks && err == cudaSuccess; i += chunk_of[k], ++k) {
+    const int64_t cb = chunk_of[k];
     float* xh = p->xhat_all + i * out_clip;
     ok(cudaStreamWaitEvent(p->run, p->x_ready[k], 0));
     ok(ac::mdct_forward(p->mdct->tb, p->x_all + i * in_clip, p->y, cb, blocks, c, p->run));
