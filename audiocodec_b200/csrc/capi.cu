@@ -458,12 +458,37 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
           job_start[static_cast<size_t>(c) * 9 + (++w)] = static_cast<int32_t>(first_job + j + 1);
       }
       while (w < 8) job_start[static_cast<size_t>(c) * 9 + (++w)] = static_cast<int32_t>(job_desc.size());
+      // tonality pass of the chunk (~9 instructions per filter): contiguous runs that level the warps' totals
+      if (c < ac::kPaMaxChunks) {
+        double load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int ww = 0; ww < 8; ++ww)
+          for (int j = job_start[static_cast<size_t>(c) * 9 + ww]; j < job_start[static_cast<size_t>(c) * 9 + ww + 1]; ++j)
+            load[ww] += cost[static_cast<size_t>(j) - first_job];
+        const int rows = kc1 - kc0;
+        const double row_cost = 9.0;
+        // water-filling: the level T with sum_w max(0, T - load_w) = rows * row_cost
+        double lo = 0, hi = total + rows * row_cost;
+        for (int it = 0; it < 60; ++it) {
+          const double mid = 0.5 * (lo + hi);
+          double fill = 0;
+          for (double l : load) fill += std::max(0.0, mid - l);
+          (fill < rows * row_cost ? lo : hi) = mid;
+        }
+        int at = 0;
+        for (int ww = 0; ww < 8; ++ww) {
+          plan->jobs.ton_start[c * 9 + ww] = static_cast<int16_t>(at);
+          int take = static_cast<int>(std::lround(std::max(0.0, hi - load[ww]) / row_cost));
+          take = std::min(take, rows - at);
+          if (ww == 7) take = rows - at;
+          at += take;
+        }
+        plan->jobs.ton_start[c * 9 + 8] = static_cast<int16_t>(rows);
+      }
     }
     job_start[static_cast<size_t>(d.mma_n_chunks) * 9] = static_cast<int32_t>(job_desc.size());
     d.n_jobs = static_cast<int>(job_desc.size());
     d.n_mma_w4 = static_cast<int>(mma_w4.size());
     if (d.n_jobs <= ac::kPaMaxJobs && d.mma_n_chunks <= ac::kPaMaxChunks) {
-      std::memset(&plan->jobs, 0, sizeof(plan->jobs));
       std::copy(job_desc.begin(), job_desc.end(), plan->jobs.job);
       std::copy(job_start.begin(), job_start.end(), plan->jobs.start);
       d.jobs_host = &plan->jobs;

@@ -49,6 +49,8 @@ constexpr int kPaMaxJobs = 112, kPaMaxChunks = 32;
 struct PaJobParams {
   int4 job[kPaMaxJobs];
   int32_t start[9 * kPaMaxChunks + 1];
+  // tonality pass: warp w of chunk c sums the filters ton_start[9 c + w] .. ton_start[9 c + w + 1] of the chunk
+  int16_t ton_start[9 * kPaMaxChunks + 2];
 };
 
 // Device-resident psychoacoustic tables (psychoacoustic.py:52-69, sparse forms from tables.h).

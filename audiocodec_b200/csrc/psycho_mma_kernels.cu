@@ -486,20 +486,20 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
           unpack2(in2, ix, iy);
           return pack2(fmaxf(eps, ix), fmaxf(eps, iy));
         };
-        int k = warp;
-        if (kcn == 64) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const u64 a2 = lds_t(warp + 16 * u), b2 = lds_t(warp + 16 * u + 8);
-            const u64 ia = fmul2(a2, a2), ib = fmul2(b2, b2);
-            ton_i2 = fadd2(ton_i2, fadd2(ia, ib));
-            float px, py;
-            unpack2(fmul2(clamp2(ia), clamp2(ib)), px, py);
-            ton_l2 = fadd2(ton_l2, pack2(lg2_approx(px), lg2_approx(py)));
-          }
-          k = kcn;
+        // the filters of the chunk are dealt to the warps in contiguous runs that even out the band-sum jobs below
+        // (PaJobParams::ton_start): a warp with few or no jobs in this chunk takes more of the tonality pass
+        int k = jp.ton_start[chunk * 9 + warp_u];
+        const int k1 = jp.ton_start[chunk * 9 + warp_u + 1];
+#pragma unroll 2
+        for (; k + 1 < k1; k += 2) {
+          const u64 a2 = lds_t(k), b2 = lds_t(k + 1);
+          const u64 ia = fmul2(a2, a2), ib = fmul2(b2, b2);
+          ton_i2 = fadd2(ton_i2, fadd2(ia, ib));
+          float px, py;
+          unpack2(fmul2(clamp2(ia), clamp2(ib)), px, py);
+          ton_l2 = fadd2(ton_l2, pack2(lg2_approx(px), lg2_approx(py)));
         }
-        for (; k < kcn; k += kWarps) {
+        if (k < k1) {
           const u64 a2 = lds_t(k);
           const u64 in2 = fmul2(a2, a2);
           float ix, iy;
