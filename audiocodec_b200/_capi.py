@@ -43,6 +43,13 @@ SIGNATURES = {
   "ac_pa_add_noise_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, ctypes.c_uint64, _c_void_p]),
   "ac_quantize_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
   "ac_dequantize_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
+  "ac_mdct_forward_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
+  "ac_mdct_inverse_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
+  "ac_pa_tonality_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
+  "ac_pa_threshold_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, ctypes.c_double, _c_void_p, _c_int64,
+                                         _c_int64, ctypes.c_int, _c_void_p]),
+  "ac_quantize_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
+  "ac_dequantize_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
   "ac_codec_pipeline_create": (ctypes.c_int, [_c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int,
                                               ctypes.POINTER(_c_void_p)]),
   "ac_codec_pipeline_destroy": (ctypes.c_int, [_c_void_p]),

@@ -10,13 +10,15 @@ import torch
 
 
 def normalise_compute_dtype(dtype, who):
-  """Accepts tf / torch / numpy dtypes or strings; only float32 compute is built."""
+  """Accepts tf / torch / numpy dtypes or strings; float32 (the tuned path) and float64 (functional kernels) are built."""
   name = getattr(dtype, "name", None) or str(dtype)
   name = name.replace("torch.", "").replace("<dtype: '", "").replace("'>", "")
   if name in ("float32", "float", "f32") or dtype is np.float32:
     return "float32"
-  if name in ("float64", "double", "bfloat16"):
-    raise NotImplementedError(f"{who}: compute_dtype {name} is accepted by the reference but only float32 kernels are built")
+  if name in ("float64", "double", "f64") or dtype is np.float64:
+    return "float64"
+  if name == "bfloat16":
+    raise NotImplementedError(f"{who}: compute_dtype bfloat16 is accepted by the reference but no bfloat16 kernels are built")
   raise TypeError(f"compute_dtype of {who} should be float64, float32 or bfloat16 (got {dtype!r})")
 
 
@@ -50,6 +52,10 @@ def adopt(x, name, dtype=torch.float32):
   if x.data_ptr() % 16 != 0:
     x = x.clone()
   return x, back
+
+
+def torch_dtype(name):
+  return torch.float64 if name == "float64" else torch.float32
 
 
 def stream_ptr(device):

@@ -76,12 +76,14 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 struct ac_mdct_plan {
   int device = 0;
   ac::MdctDeviceTables tb;
+  ac::MdctDeviceTables64 tb64;
   std::vector<void*> owned;
 };
 
 struct ac_pa_plan {
   int device = 0;
   ac::PaDeviceTables tb;
+  ac::PaDeviceTables64 tb64;
   ac::PaJobParams jobs;
   ac::PaTables host;
   std::vector<void*> owned;
@@ -281,6 +283,21 @@ int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_m
     free_all(plan->owned);
     delete plan;
     return cuda_fail(err, "uploading MDCT tables");
+  }
+  // float64 compute dtype (f64_kernels.cu): the unrounded tables
+  {
+    std::vector<double> cos64(static_cast<size_t>(8) * n);
+    for (int m = 0; m < 8 * n; ++m) cos64[m] = std::cos(pi * m / (4.0 * n));
+    plan->tb64.n = n;
+    plan->tb64.scale_fwd = scale_fwd;
+    plan->tb64.scale_inv = scale_inv;
+    if ((err = upload(t.fold, &plan->tb64.fold, plan->owned)) != cudaSuccess ||
+        (err = upload(t.unfold, &plan->tb64.unfold, plan->owned)) != cudaSuccess ||
+        (err = upload(cos64, &plan->tb64.cos_table, plan->owned)) != cudaSuccess) {
+      free_all(plan->owned);
+      delete plan;
+      return cuda_fail(err, "uploading the float64 MDCT tables");
+    }
   }
   *out = plan;
   return AC_OK;
@@ -552,6 +569,40 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
     delete plan;
     return cuda_fail(err, "uploading psychoacoustic tables");
   }
+  // float64 compute dtype (f64_kernels.cu): unrounded weights; the index arrays are shared with the fp32 plan
+  {
+    ac::PaDeviceTables64& e = plan->tb64;
+    e.n = t.n;
+    e.nb = t.nb;
+    e.alpha = alpha;
+    e.inv_alpha = 1. / alpha;
+    e.eps = 1e-14;
+    e.band_k0 = d.band_k0;
+    e.band_cnt = d.band_cnt;
+    e.band_ptr = d.band_ptr;
+    e.filt_b0 = d.filt_b0;
+    e.filt_cnt = d.filt_cnt;
+    e.filt_ptr = d.filt_ptr;
+    std::vector<double> band_w64, filt_w64, lin64(t.nb, 0.0);
+    for (int i = 0; i < t.nb; ++i)
+      for (int k = t.band_k0[i]; k < t.band_k0[i] + t.band_cnt[i]; ++k) band_w64.push_back(t.w[static_cast<size_t>(k) * t.nb + i]);
+    for (int k = 0; k < t.n; ++k)
+      for (int i = t.filt_b0[k]; i < t.filt_b0[k] + t.filt_cnt[k]; ++i) filt_w64.push_back(t.w_inv[static_cast<size_t>(i) * t.n + k]);
+    if (t.nb > 1) {                                        // tf.linspace(0, max_bark, nb) in float64 (:187-189)
+      const double delta = t.max_bark / (t.nb - 1);
+      for (int j = 0; j < t.nb; ++j) lin64[j] = j * delta;
+      lin64[t.nb - 1] = t.max_bark;
+    }
+    if ((err = upload(band_w64, &e.band_w, plan->owned)) != cudaSuccess ||
+        (err = upload(filt_w64, &e.filt_w, plan->owned)) != cudaSuccess ||
+        (err = upload(t.quiet, &e.quiet, plan->owned)) != cudaSuccess ||
+        (err = upload(t.spread_fn, &e.spread_fn, plan->owned)) != cudaSuccess ||
+        (err = upload(lin64, &e.lin, plan->owned)) != cudaSuccess) {
+      free_all(plan->owned);
+      delete plan;
+      return cuda_fail(err, "uploading the float64 psychoacoustic tables");
+    }
+  }
   *out = plan;
   return AC_OK;
 }
@@ -793,6 +844,61 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
     stats[2] = static_cast<double>(host_stats[2]) / 65536.0;
   }
   return AC_OK;
+}
+
+// ------------------------------------------------------------------------------------ float64 compute dtype
+int ac_mdct_forward_f64(const ac_mdct_plan* plan, const double* x, double* y, int64_t batches, int64_t samples,
+                        int channels, void* stream) {
+  if (int rc = check_common(plan, batches, samples, channels)) return rc;
+  const int n = plan->tb64.n;
+  if (samples % n != 0)
+    return fail(AC_ERR_INVALID, "samples_n (%lld) must be a multiple of filters_n (%d)", (long long)samples, n);
+  if (batches == 0) return AC_OK;
+  if ((x == nullptr && samples > 0) || y == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::mdct_forward_f64(plan->tb64, x, y, batches, samples / n, channels, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "mdct_forward_f64 launch");
+}
+
+int ac_mdct_inverse_f64(const ac_mdct_plan* plan, const double* y, double* x, int64_t batches, int64_t blocks,
+                        int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (batches == 0) return AC_OK;
+  if ((y == nullptr && blocks > 0) || x == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::mdct_inverse_f64(plan->tb64, y, x, batches, blocks, channels, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "mdct_inverse_f64 launch");
+}
+
+int ac_pa_tonality_f64(const ac_pa_plan* plan, const double* y, double* ton, int64_t batches, int64_t blocks,
+                       int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (batches * blocks == 0) return AC_OK;
+  if (y == nullptr || ton == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::pa_tonality_f64(plan->tb64, y, ton, batches * blocks, channels, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_tonality_f64 launch");
+}
+
+int ac_pa_threshold_f64(const ac_pa_plan* plan, const double* y, const double* ton, double drown, double* thr,
+                        int64_t batches, int64_t blocks, int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (batches * blocks == 0) return AC_OK;
+  if (y == nullptr || thr == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::pa_threshold_f64(plan->tb64, y, ton, drown, thr, batches * blocks, channels,
+                                         static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_threshold_f64 launch");
+}
+
+int ac_quantize_f64(const double* y, const double* thr, int32_t* q, int64_t n, void* stream) {
+  if (n < 0) return fail(AC_ERR_INVALID, "negative size");
+  if (n > 0 && (y == nullptr || thr == nullptr || q == nullptr)) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::quantize_f64(y, thr, q, n, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "quantize_f64 launch");
+}
+
+int ac_dequantize_f64(const int32_t* q, const double* thr, double* y, int64_t n, void* stream) {
+  if (n < 0) return fail(AC_ERR_INVALID, "negative size");
+  if (n > 0 && (y == nullptr || thr == nullptr || q == nullptr)) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::dequantize_f64(q, thr, y, n, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "dequantize_f64 launch");
 }
 
 // ---------------------------------------------------------------------------------------------- DLPack

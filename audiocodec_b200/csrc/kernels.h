@@ -110,6 +110,40 @@ cudaError_t pa_threshold_mma_tile(const PaDeviceTables& tb, const float* y, cons
                                   float thr_scale, float* thr_out, int32_t* q_out, int64_t frames, int channels,
                                   cudaStream_t stream);
 
+// float64 compute dtype (f64_kernels.cu): the same tables in double, sparse forms shared with the fp32 plan
+struct MdctDeviceTables64 {
+  int n = 0;
+  double scale_fwd = 0., scale_inv = 0.;
+  const double* fold = nullptr;        // [4 N/2]
+  const double* unfold = nullptr;      // [4 N/2]
+  const double* cos_table = nullptr;   // [8N] cos(pi m / (4N))
+};
+struct PaDeviceTables64 {
+  int n = 0, nb = 0;
+  double alpha = 0., inv_alpha = 0., eps = 1e-14;
+  const int32_t* band_k0 = nullptr;
+  const int32_t* band_cnt = nullptr;
+  const int32_t* band_ptr = nullptr;
+  const double* band_w = nullptr;
+  const int32_t* filt_b0 = nullptr;
+  const int32_t* filt_cnt = nullptr;
+  const int32_t* filt_ptr = nullptr;
+  const double* filt_w = nullptr;
+  const double* quiet = nullptr;
+  const double* spread_fn = nullptr;
+  const double* lin = nullptr;
+};
+cudaError_t mdct_forward_f64(const MdctDeviceTables64& tb, const double* x, double* y, int64_t batches, int64_t blocks_n,
+                             int channels, cudaStream_t stream);
+cudaError_t mdct_inverse_f64(const MdctDeviceTables64& tb, const double* y, double* x, int64_t batches, int64_t frames_n,
+                             int channels, cudaStream_t stream);
+cudaError_t pa_tonality_f64(const PaDeviceTables64& tb, const double* y, double* ton, int64_t rows, int channels,
+                            cudaStream_t stream);
+cudaError_t pa_threshold_f64(const PaDeviceTables64& tb, const double* y, const double* ton_in, double drown, double* thr,
+                             int64_t rows, int channels, cudaStream_t stream);
+cudaError_t quantize_f64(const double* y, const double* thr, int32_t* q, int64_t n, cudaStream_t stream);
+cudaError_t dequantize_f64(const int32_t* q, const double* thr, double* y, int64_t n, cudaStream_t stream);
+
 void count_launch();
 int tile_sm_count();
 

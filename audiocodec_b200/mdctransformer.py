@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._tensors import adopt, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr
+from ._tensors import adopt, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr, torch_dtype
 
 
 class MDCTransformer:
@@ -20,13 +20,16 @@ class MDCTransformer:
 
     :param filters_n:        number of filter bands (needs to be even; AssertionError otherwise, :26)
     :param window_type:      'sine', 'vorbis' (default); any other string selects the rectangular window (:199-211)
-    :param compute_dtype:    dtype of inputs and outputs; only float32 is built (tf / torch / numpy dtype or string)
+    :param compute_dtype:    dtype of inputs and outputs (tf / torch / numpy dtype or string): float32 (the tuned
+                             tile kernels) or float64 (functional kernels); bfloat16 raises NotImplementedError
     :param precompute_dtype: float64 (default) or float32 for the window tables (:58-59)
     """
     assert (filters_n % 2) == 0, "number of filters used in mdct transformation needs to be even"
     self.filters_n = int(filters_n)
     self.window_type = window_type
     self.compute_dtype = normalise_compute_dtype(compute_dtype, "MDCTransformer")
+    self._dtype = torch_dtype(self.compute_dtype)
+    self._sfx = "f64" if self.compute_dtype == "float64" else "f32"
     self._precompute_f32 = int(normalise_precompute_dtype(precompute_dtype) == "float32")
     kind = window_type.lower()   # window_type=None fails here exactly like the reference (:199)
     self._window_code = {"sine": _capi.WINDOW_SINE, "vorbis": _capi.WINDOW_VORBIS}.get(kind, _capi.WINDOW_ONES)
@@ -95,16 +98,16 @@ class MDCTransformer:
     :return:  [batches_n, blocks_n + 1, filters_n, channels_n] with samples_n = blocks_n * filters_n
     :raises ValueError: samples_n is not a multiple of filters_n (the reference raises InvalidArgumentError, :287)
     """
-    x, back = adopt(x, "x")
+    x, back = adopt(x, "x", dtype=self._dtype)
     if x.dim() != 3:
       raise ValueError(f"x must be [batches_n, samples_n, channels_n], got shape {tuple(x.shape)}")
     b, s, c = x.shape
     if s % self.filters_n != 0:
       raise ValueError(f"samples_n ({s}) must be a multiple of filters_n ({self.filters_n})")
-    y = torch.empty((b, s // self.filters_n + 1, self.filters_n, c), dtype=torch.float32, device=x.device)
+    y = torch.empty((b, s // self.filters_n + 1, self.filters_n, c), dtype=self._dtype, device=x.device)
     with torch.cuda.device(x.device):
-      _capi.check(_capi.lib().ac_mdct_forward_f32(self._plan(x.device), x.data_ptr(), y.data_ptr(), b, s, c,
-                                                  stream_ptr(x.device)))
+      forward = getattr(_capi.lib(), "ac_mdct_forward_" + self._sfx)
+      _capi.check(forward(self._plan(x.device), x.data_ptr(), y.data_ptr(), b, s, c, stream_ptr(x.device)))
     return back(y)
 
   def inverse_transform(self, mdct_amplitudes):
@@ -113,14 +116,14 @@ class MDCTransformer:
     :param mdct_amplitudes: [batches_n, blocks_n, filters_n, channels_n], float32, CUDA
     :return:                [batches_n, (blocks_n + 1) * filters_n, channels_n]
     """
-    y, back = adopt(mdct_amplitudes, "mdct_amplitudes")
+    y, back = adopt(mdct_amplitudes, "mdct_amplitudes", dtype=self._dtype)
     if y.dim() != 4 or y.shape[2] != self.filters_n:
       raise ValueError(f"mdct_amplitudes must be [batches_n, blocks_n, {self.filters_n}, channels_n], got {tuple(y.shape)}")
     b, m, n, c = y.shape
-    x = torch.empty((b, (m + 1) * n, c), dtype=torch.float32, device=y.device)
+    x = torch.empty((b, (m + 1) * n, c), dtype=self._dtype, device=y.device)
     with torch.cuda.device(y.device):
-      _capi.check(_capi.lib().ac_mdct_inverse_f32(self._plan(y.device), y.data_ptr(), x.data_ptr(), b, m, c,
-                                                  stream_ptr(y.device)))
+      inverse = getattr(_capi.lib(), "ac_mdct_inverse_" + self._sfx)
+      _capi.check(inverse(self._plan(y.device), y.data_ptr(), x.data_ptr(), b, m, c, stream_ptr(y.device)))
     return back(x)
 
   def inverse_transform_dequantized(self, q, masking_threshold):
@@ -130,10 +133,16 @@ class MDCTransformer:
     :param masking_threshold: float32 quantiser step, same shape
     """
     q, _ = adopt(q, "q", dtype=torch.int32)
-    thr, back = adopt(masking_threshold, "masking_threshold")
+    thr, back = adopt(masking_threshold, "masking_threshold", dtype=self._dtype)
     if q.dim() != 4 or q.shape[2] != self.filters_n or q.shape != thr.shape:
       raise ValueError("q and masking_threshold must both be [batches_n, blocks_n, filters_n, channels_n]")
     b, m, n, c = q.shape
+    if self.compute_dtype == "float64":       # two kernels: dequantise, then the float64 inverse transform
+      amplitudes = torch.empty_like(thr)
+      with torch.cuda.device(q.device):
+        _capi.check(_capi.lib().ac_dequantize_f64(q.data_ptr(), thr.data_ptr(), amplitudes.data_ptr(), q.numel(),
+                                                  stream_ptr(q.device)))
+      return back(self.inverse_transform(amplitudes))
     x = torch.empty((b, (m + 1) * n, c), dtype=torch.float32, device=q.device)
     with torch.cuda.device(q.device):
       _capi.check(_capi.lib().ac_mdct_inverse_dequant_f32(self._plan(q.device), q.data_ptr(), thr.data_ptr(),

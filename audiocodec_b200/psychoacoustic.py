@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._tensors import adopt, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr
+from ._tensors import torch_dtype, adopt, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr
 
 
 class PsychoacousticModel:
@@ -20,13 +20,15 @@ class PsychoacousticModel:
     """Same arguments as the reference (psychoacoustic.py:14-15).
 
     :raises TypeError: compute_dtype outside {float64, float32, bfloat16} (:42-43)
-    :raises NotImplementedError: float64 / bfloat16 compute (only float32 kernels are built)
+    :raises NotImplementedError: bfloat16 compute (float32 is the tuned path, float64 runs functional kernels)
     """
     self.alpha = alpha
     self.sample_rate = sample_rate
     self.bark_bands_n = int(bark_bands_n)
     self.filter_bands_n = int(filter_bands_n)
     self.compute_dtype = normalise_compute_dtype(compute_dtype, "PsychoacousticModel")
+    self._dtype = torch_dtype(self.compute_dtype)
+    self._f64 = self.compute_dtype == "float64"
     if normalise_precompute_dtype(precompute_dtype) != "float64":
       raise NotImplementedError("PsychoacousticModel tables are precomputed in float64")
 
@@ -100,13 +102,13 @@ class PsychoacousticModel:
     :param mdct_amplitudes: [batches_n, blocks_n, filter_bands_n, channels_n], float32, CUDA
     :return:                [batches_n, blocks_n, 1, channels_n]
     """
-    a, back = adopt(mdct_amplitudes, "mdct_amplitudes")
+    a, back = adopt(mdct_amplitudes, "mdct_amplitudes", dtype=self._dtype)
     self._check_amplitudes(a)
     b, m, _, c = a.shape
-    ton = torch.empty((b, m, 1, c), dtype=torch.float32, device=a.device)
+    ton = torch.empty((b, m, 1, c), dtype=self._dtype, device=a.device)
     with torch.cuda.device(a.device):
-      _capi.check(_capi.lib().ac_pa_tonality_f32(self._plan(a.device), a.data_ptr(), ton.data_ptr(), b, m, c,
-                                                 stream_ptr(a.device)))
+      tonality = _capi.lib().ac_pa_tonality_f64 if self._f64 else _capi.lib().ac_pa_tonality_f32
+      _capi.check(tonality(self._plan(a.device), a.data_ptr(), ton.data_ptr(), b, m, c, stream_ptr(a.device)))
     return back(ton)
 
   def global_masking_threshold(self, mdct_amplitudes, tonality_per_block, drown=0.0):
@@ -117,23 +119,26 @@ class PsychoacousticModel:
     :param drown:              0..1, python float
     :return:                   [batches_n, blocks_n, filter_bands_n, channels_n], never below 1e-7
     """
-    a, back = adopt(mdct_amplitudes, "mdct_amplitudes")
+    a, back = adopt(mdct_amplitudes, "mdct_amplitudes", dtype=self._dtype)
     self._check_amplitudes(a)
     b, m, _, c = a.shape
     ton_ptr = None
     if tonality_per_block is not None:
-      ton, _ = adopt(tonality_per_block, "tonality_per_block")
+      ton, _ = adopt(tonality_per_block, "tonality_per_block", dtype=self._dtype)
       if tuple(ton.shape) != (b, m, 1, c):
         raise ValueError(f"tonality_per_block must be [{b}, {m}, 1, {c}], got {tuple(ton.shape)}")
       ton_ptr = ton.data_ptr()
     thr = torch.empty_like(a)
     with torch.cuda.device(a.device):
-      _capi.check(_capi.lib().ac_pa_threshold_f32(self._plan(a.device), a.data_ptr(), ton_ptr, float(drown),
-                                                  thr.data_ptr(), b, m, c, stream_ptr(a.device)))
+      threshold = _capi.lib().ac_pa_threshold_f64 if self._f64 else _capi.lib().ac_pa_threshold_f32
+      _capi.check(threshold(self._plan(a.device), a.data_ptr(), ton_ptr, float(drown), thr.data_ptr(), b, m, c,
+                            stream_ptr(a.device)))
     return back(thr)
 
   def add_noise(self, mdct_amplitudes, masking_threshold, seed=None):
     """mdct_amplitudes + masking_threshold * N(0, 1/6) (psychoacoustic.py:150-167), Philox counter RNG."""
+    if self._f64:
+      raise NotImplementedError("add_noise is built for float32 only")
     a, back = adopt(mdct_amplitudes, "mdct_amplitudes")
     thr, _ = adopt(masking_threshold, "masking_threshold")
     if a.shape != thr.shape:
@@ -149,26 +154,26 @@ class PsychoacousticModel:
   # ---- quantiser (build-defined: the reference has none) ---------------------------
   def quantize(self, mdct_amplitudes, masking_threshold):
     """q = rint(A / thr), int32 (IEEE divide, round-half-even)."""
-    a, _ = adopt(mdct_amplitudes, "mdct_amplitudes")
-    thr, _ = adopt(masking_threshold, "masking_threshold")
+    a, _ = adopt(mdct_amplitudes, "mdct_amplitudes", dtype=self._dtype)
+    thr, _ = adopt(masking_threshold, "masking_threshold", dtype=self._dtype)
     if a.shape != thr.shape:
       raise ValueError("masking_threshold must have the shape of mdct_amplitudes")
     q = torch.empty(a.shape, dtype=torch.int32, device=a.device)
     with torch.cuda.device(a.device):
-      _capi.check(_capi.lib().ac_quantize_f32(a.data_ptr(), thr.data_ptr(), q.data_ptr(), a.numel(),
-                                              stream_ptr(a.device)))
+      quantize = _capi.lib().ac_quantize_f64 if self._f64 else _capi.lib().ac_quantize_f32
+      _capi.check(quantize(a.data_ptr(), thr.data_ptr(), q.data_ptr(), a.numel(), stream_ptr(a.device)))
     return q
 
   def dequantize(self, q, masking_threshold):
     """A_hat = q * thr."""
     q, _ = adopt(q, "q", dtype=torch.int32)
-    thr, back = adopt(masking_threshold, "masking_threshold")
+    thr, back = adopt(masking_threshold, "masking_threshold", dtype=self._dtype)
     if q.shape != thr.shape:
       raise ValueError("masking_threshold must have the shape of q")
     out = torch.empty_like(thr)
     with torch.cuda.device(q.device):
-      _capi.check(_capi.lib().ac_dequantize_f32(q.data_ptr(), thr.data_ptr(), out.data_ptr(), q.numel(),
-                                                stream_ptr(q.device)))
+      dequantize = _capi.lib().ac_dequantize_f64 if self._f64 else _capi.lib().ac_dequantize_f32
+      _capi.check(dequantize(q.data_ptr(), thr.data_ptr(), out.data_ptr(), q.numel(), stream_ptr(q.device)))
     return back(out)
 
   def encode(self, mdct_amplitudes, drown=0.0, thr_scale=1.0, return_threshold=True):
@@ -176,6 +181,12 @@ class PsychoacousticModel:
 
     :return: (q int32, step float32) with step = thr_scale * threshold, or q alone.
     """
+    if self._f64:                             # no fused float64 kernel: threshold (internal tonality), then quantise
+      if float(thr_scale) != 1.0:
+        raise NotImplementedError("thr_scale != 1 is built for float32 only")
+      thr = self.global_masking_threshold(mdct_amplitudes, None, drown=drown)
+      q = self.quantize(mdct_amplitudes, thr)
+      return (q, thr) if return_threshold else q
     a, _ = adopt(mdct_amplitudes, "mdct_amplitudes")
     self._check_amplitudes(a)
     b, m, _, c = a.shape

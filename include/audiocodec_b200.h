@@ -118,6 +118,21 @@ int ac_pa_add_noise_f32(const float* y, const float* thr, float* out, int64_t n,
 int ac_quantize_f32(const float* y, const float* thr, int32_t* q, int64_t n, void* stream);
 int ac_dequantize_f32(const int32_t* q, const float* thr, float* y, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------- float64 compute dtype */
+/* The reference accepts compute_dtype=tf.float64 for both classes (mdctransformer.py:13-23,
+ * psychoacoustic.py:42-44).  Same operations and layouts as the _f32 entry points on float64 tensors with the
+ * unrounded float64 tables; functional kernels (any even filters_n), not the tuned fp32 path. */
+int ac_mdct_forward_f64(const ac_mdct_plan* plan, const double* x, double* y,
+                        int64_t batches, int64_t samples, int channels, void* stream);
+int ac_mdct_inverse_f64(const ac_mdct_plan* plan, const double* y, double* x,
+                        int64_t batches, int64_t blocks, int channels, void* stream);
+int ac_pa_tonality_f64(const ac_pa_plan* plan, const double* y, double* ton,
+                       int64_t batches, int64_t blocks, int channels, void* stream);
+int ac_pa_threshold_f64(const ac_pa_plan* plan, const double* y, const double* ton, double drown, double* thr,
+                        int64_t batches, int64_t blocks, int channels, void* stream);
+int ac_quantize_f64(const double* y, const double* thr, int32_t* q, int64_t n, void* stream);
+int ac_dequantize_f64(const int32_t* q, const double* thr, double* y, int64_t n, void* stream);
+
 /* ------------------------------------------------------------------------- host-buffer streaming */
 /* encode + decode of clips that live in HOST memory (the call a file / network front end makes; no reference
  * symbol - the reference leaves data movement to TensorFlow).  The pipeline owns three streams, device staging

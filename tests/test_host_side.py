@@ -86,6 +86,8 @@ def test_constructor_errors_match_reference():
     audiocodec_b200.MDCTransformer(8, compute_dtype='int32')
   assert audiocodec_b200.MDCTransformer(8, compute_dtype=torch.float32).compute_dtype == "float32"
   assert audiocodec_b200.MDCTransformer(8, compute_dtype=np.float32).compute_dtype == "float32"
+  assert audiocodec_b200.MDCTransformer(8, compute_dtype=torch.float64).compute_dtype == "float64"
+  assert audiocodec_b200.PsychoacousticModel(44100, 8, compute_dtype="float64").compute_dtype == "float64"
 
 
 def test_no_cpu_path():
