@@ -26,6 +26,8 @@ SIGNATURES = {
   "ac_mdct_tables_host": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, _c_double_p, _c_double_p]),
   "ac_pa_tables_host": (ctypes.c_int, [ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                        _c_float_p, _c_float_p, _c_float_p, _c_float_p, _c_double_p]),
+  "ac_pa_mma_jobs_host": (ctypes.c_int, [ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_void_p,
+                                         _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
   "ac_mdct_plan_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_c_void_p)]),
   "ac_mdct_plan_destroy": (ctypes.c_int, [_c_void_p]),
   "ac_mdct_forward_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
@@ -43,6 +45,7 @@ SIGNATURES = {
   "ac_pa_add_noise_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, ctypes.c_uint64, _c_void_p]),
   "ac_quantize_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
   "ac_dequantize_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
+  "ac_codec_stats_i32": (ctypes.c_int, [_c_void_p, _c_int64, _c_void_p, _c_void_p]),
   "ac_mdct_forward_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
   "ac_mdct_inverse_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
   "ac_pa_tonality_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),

@@ -130,6 +130,85 @@ int unwrap_dl(struct DLManagedTensor* m, const char* name, int ndim, uint8_t cod
 
 }  // namespace
 
+// Band-sum job list of the tensor-core tile kernel (psycho_mma_kernels.cu; PaJobParams in kernels.h): chunks of 64
+// filters, one job per (band, chunk) = steps of four filters with zero-padded weights; the jobs of a chunk are dealt
+// to the eight warps in contiguous runs of equal cost, and the filters of the chunk's tonality pass in contiguous runs
+// that level the warps' totals.  Host-only (no CUDA): ac_pa_mma_jobs_host exposes it to the CPU tests.  Returns
+// false when the list does not fit the kernel parameter (the kernel is then not used).
+static bool build_mma_jobs(const ac::PaTables& t, ac::PaJobParams& jp, std::vector<float>& mma_w4, int* chunk_k,
+                           int* n_chunks_out, int* n_jobs_out) {
+  const int mma_chunk_k = 64;
+  const int mma_n_chunks = (t.n + mma_chunk_k - 1) / mma_chunk_k;
+  std::vector<int4> job_desc;
+  std::vector<int32_t> job_start(static_cast<size_t>(mma_n_chunks) * 9 + 1, 0);
+  std::vector<int16_t> ton_start(static_cast<size_t>(mma_n_chunks) * 9 + 1, 0);
+  for (int c = 0; c < mma_n_chunks; ++c) {
+    const int kc0 = c * mma_chunk_k, kc1 = std::min(t.n, kc0 + mma_chunk_k);
+    const size_t first_job = job_desc.size();
+    std::vector<double> cost;
+    for (int i = 0; i < t.nb; ++i) {
+      const int ka = std::max(t.band_k0[i], kc0), kb = std::min(t.band_k0[i] + t.band_cnt[i], kc1);
+      if (kb <= ka) continue;
+      const int steps = (kb - ka + 3) / 4;
+      const bool final = t.band_k0[i] + t.band_cnt[i] <= kc1, partial = t.band_k0[i] < kc0;
+      int4 jb;
+      jb.x = (ka - kc0) * 66 * 4;                      // byte offset of the first row of T (66 words per row)
+      jb.y = static_cast<int>(mma_w4.size()) * 8;      // byte offset of the weights, each stored twice (packed pairs)
+      jb.z = steps;
+      // byte offset of P[band][0] (64 items per band) with the XOR swizzle of the band folded in (the kernel xors
+      // 8 * lane: a lane owns the item pair 2 lane, 2 lane + 1)
+      jb.w = (i * 256 + ((i & 3) << 5)) | (partial ? 0x10000 : 0) | (final ? 0x20000 : 0);
+      for (int k = ka; k < ka + 4 * steps; ++k)
+        mma_w4.push_back(k < kb ? t.band_w[t.band_ptr[i] + (k - t.band_k0[i])] : 0.f);
+      job_desc.push_back(jb);
+      cost.push_back(13.5 * steps + (final ? 45.0 : 25.0));   // ~instructions per lane
+    }
+    double total = 0, run = 0;
+    for (double v : cost) total += v;
+    int w = 0;
+    job_start[static_cast<size_t>(c) * 9] = static_cast<int32_t>(first_job);
+    for (size_t j = 0; j < cost.size(); ++j) {
+      run += cost[j];
+      while (w < 7 && run >= total * (w + 1) / 8.0)
+        job_start[static_cast<size_t>(c) * 9 + (++w)] = static_cast<int32_t>(first_job + j + 1);
+    }
+    while (w < 8) job_start[static_cast<size_t>(c) * 9 + (++w)] = static_cast<int32_t>(job_desc.size());
+    // tonality pass of the chunk (~9 instructions per filter): water-filling, the level T with
+    // sum_w max(0, T - load_w) = rows * row_cost
+    double load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int ww = 0; ww < 8; ++ww)
+      for (int j = job_start[static_cast<size_t>(c) * 9 + ww]; j < job_start[static_cast<size_t>(c) * 9 + ww + 1]; ++j)
+        load[ww] += cost[static_cast<size_t>(j) - first_job];
+    const int rows = kc1 - kc0;
+    const double row_cost = 9.0;
+    double lo = 0, hi = total + rows * row_cost;
+    for (int it = 0; it < 60; ++it) {
+      const double mid = 0.5 * (lo + hi);
+      double fill = 0;
+      for (double l : load) fill += std::max(0.0, mid - l);
+      (fill < rows * row_cost ? lo : hi) = mid;
+    }
+    int at = 0;
+    for (int ww = 0; ww < 8; ++ww) {
+      ton_start[static_cast<size_t>(c) * 9 + ww] = static_cast<int16_t>(at);
+      int take = static_cast<int>(std::lround(std::max(0.0, hi - load[ww]) / row_cost));
+      take = std::min(take, rows - at);
+      if (ww == 7) take = rows - at;
+      at += take;
+    }
+    ton_start[static_cast<size_t>(c) * 9 + 8] = static_cast<int16_t>(rows);
+  }
+  job_start[static_cast<size_t>(mma_n_chunks) * 9] = static_cast<int32_t>(job_desc.size());
+  *chunk_k = mma_chunk_k;
+  *n_chunks_out = mma_n_chunks;
+  *n_jobs_out = static_cast<int>(job_desc.size());
+  if (static_cast<int>(job_desc.size()) > ac::kPaMaxJobs || mma_n_chunks > ac::kPaMaxChunks) return false;
+  std::copy(job_desc.begin(), job_desc.end(), jp.job);
+  std::copy(job_start.begin(), job_start.end(), jp.start);
+  std::copy(ton_start.begin(), ton_start.end(), jp.ton_start);
+  return true;
+}
+
 extern "C" {
 
 const char* ac_last_error(void) { return g_error; }
@@ -170,6 +249,38 @@ int ac_pa_tables_host(double sample_rate, int filter_bands_n, int bark_bands_n, 
     scalars[3] = t.db_min;
   }
   (void)n;
+  return AC_OK;
+}
+
+int ac_pa_mma_jobs_host(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha, int32_t* jobs,
+                        int32_t* job_start, int16_t* ton_start, float* weights, int32_t* counts) {
+  if (!(sample_rate > 0) || filter_bands_n < 1 || bark_bands_n < 1 || !(alpha > 0))
+    return fail(AC_ERR_INVALID, "invalid psychoacoustic parameters");
+  if (counts == nullptr) return fail(AC_ERR_INVALID, "counts is null");
+  const ac::PaTables t = ac::build_pa_tables(sample_rate, filter_bands_n, bark_bands_n, alpha);
+  std::vector<float> w4;
+  ac::PaJobParams* jp = new (std::nothrow) ac::PaJobParams();
+  if (jp == nullptr) return fail(AC_ERR_ALLOC, "out of host memory");
+  int chunk_k = 0, n_chunks = 0, n_jobs = 0;
+  const bool fits = build_mma_jobs(t, *jp, w4, &chunk_k, &n_chunks, &n_jobs);
+  counts[0] = chunk_k;
+  counts[1] = n_chunks;
+  counts[2] = n_jobs;
+  counts[3] = static_cast<int32_t>(w4.size());
+  counts[4] = fits ? 1 : 0;
+  if (fits) {
+    if (jobs != nullptr)
+      for (int j = 0; j < n_jobs; ++j) {
+        jobs[4 * j + 0] = jp->job[j].x;
+        jobs[4 * j + 1] = jp->job[j].y;
+        jobs[4 * j + 2] = jp->job[j].z;
+        jobs[4 * j + 3] = jp->job[j].w;
+      }
+    if (job_start != nullptr) std::copy(jp->start, jp->start + 9 * n_chunks + 1, job_start);
+    if (ton_start != nullptr) std::copy(jp->ton_start, jp->ton_start + 9 * n_chunks + 1, ton_start);
+    if (weights != nullptr) std::copy(w4.begin(), w4.end(), weights);
+  }
+  delete jp;
   return AC_OK;
 }
 
@@ -436,81 +547,10 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
   desc_start[static_cast<size_t>(d.n_chunks) * 5] = static_cast<int32_t>(band_desc.size());
   d.n_desc = static_cast<int>(band_desc.size());
   d.n_band_w4 = static_cast<int>(band_w4.size());
-  // ---- tensor-core tile kernel: chunks of 64 filters, one job per (band, chunk) = steps of four filters with
-  //      zero-padded weights; the jobs of a chunk are dealt to the eight warps in contiguous runs of equal cost
+  // ---- tensor-core tile kernel: job list, tonality ranges and step weights (build_mma_jobs above)
   std::vector<float> mma_w4;
-  {
-    d.mma_chunk_k = 64;
-    d.mma_n_chunks = (t.n + d.mma_chunk_k - 1) / d.mma_chunk_k;
-    std::vector<int4> job_desc;
-    std::vector<int32_t> job_start(static_cast<size_t>(d.mma_n_chunks) * 9 + 1, 0);
-    for (int c = 0; c < d.mma_n_chunks; ++c) {
-      const int kc0 = c * d.mma_chunk_k, kc1 = std::min(t.n, kc0 + d.mma_chunk_k);
-      const size_t first_job = job_desc.size();
-      std::vector<double> cost;
-      for (int i = 0; i < t.nb; ++i) {
-        const int ka = std::max(t.band_k0[i], kc0), kb = std::min(t.band_k0[i] + t.band_cnt[i], kc1);
-        if (kb <= ka) continue;
-        const int steps = (kb - ka + 3) / 4;
-        const bool final = t.band_k0[i] + t.band_cnt[i] <= kc1, partial = t.band_k0[i] < kc0;
-        int4 jb;
-        jb.x = (ka - kc0) * 66 * 4;                      // byte offset of the first row of T (66 words per row)
-        jb.y = static_cast<int>(mma_w4.size()) * 8;      // byte offset of the weights, each stored twice (packed pairs)
-        jb.z = steps;
-        // byte offset of P[band][0] (64 items per band) with the XOR swizzle of the band folded in (the kernel xors
-        // 8 * lane: a lane owns the item pair 2 lane, 2 lane + 1)
-        jb.w = (i * 256 + ((i & 3) << 5)) | (partial ? 0x10000 : 0) | (final ? 0x20000 : 0);
-        for (int k = ka; k < ka + 4 * steps; ++k)
-          mma_w4.push_back(k < kb ? t.band_w[t.band_ptr[i] + (k - t.band_k0[i])] : 0.f);
-        job_desc.push_back(jb);
-        cost.push_back(13.5 * steps + (final ? 45.0 : 25.0));   // ~instructions per lane
-      }
-      double total = 0, run = 0;
-      for (double v : cost) total += v;
-      int w = 0;
-      job_start[static_cast<size_t>(c) * 9] = static_cast<int32_t>(first_job);
-      for (size_t j = 0; j < cost.size(); ++j) {
-        run += cost[j];
-        while (w < 7 && run >= total * (w + 1) / 8.0)
-          job_start[static_cast<size_t>(c) * 9 + (++w)] = static_cast<int32_t>(first_job + j + 1);
-      }
-      while (w < 8) job_start[static_cast<size_t>(c) * 9 + (++w)] = static_cast<int32_t>(job_desc.size());
-      // tonality pass of the chunk (~9 instructions per filter): contiguous runs that level the warps' totals
-      if (c < ac::kPaMaxChunks) {
-        double load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int ww = 0; ww < 8; ++ww)
-          for (int j = job_start[static_cast<size_t>(c) * 9 + ww]; j < job_start[static_cast<size_t>(c) * 9 + ww + 1]; ++j)
-            load[ww] += cost[static_cast<size_t>(j) - first_job];
-        const int rows = kc1 - kc0;
-        const double row_cost = 9.0;
-        // water-filling: the level T with sum_w max(0, T - load_w) = rows * row_cost
-        double lo = 0, hi = total + rows * row_cost;
-        for (int it = 0; it < 60; ++it) {
-          const double mid = 0.5 * (lo + hi);
-          double fill = 0;
-          for (double l : load) fill += std::max(0.0, mid - l);
-          (fill < rows * row_cost ? lo : hi) = mid;
-        }
-        int at = 0;
-        for (int ww = 0; ww < 8; ++ww) {
-          plan->jobs.ton_start[c * 9 + ww] = static_cast<int16_t>(at);
-          int take = static_cast<int>(std::lround(std::max(0.0, hi - load[ww]) / row_cost));
-          take = std::min(take, rows - at);
-          if (ww == 7) take = rows - at;
-          at += take;
-        }
-        plan->jobs.ton_start[c * 9 + 8] = static_cast<int16_t>(rows);
-      }
-    }
-    job_start[static_cast<size_t>(d.mma_n_chunks) * 9] = static_cast<int32_t>(job_desc.size());
-    d.n_jobs = static_cast<int>(job_desc.size());
-    d.n_mma_w4 = static_cast<int>(mma_w4.size());
-    if (d.n_jobs <= ac::kPaMaxJobs && d.mma_n_chunks <= ac::kPaMaxChunks) {
-      std::copy(job_desc.begin(), job_desc.end(), plan->jobs.job);
-      std::copy(job_start.begin(), job_start.end(), plan->jobs.start);
-      d.jobs_host = &plan->jobs;
-    }
-  }
+  if (build_mma_jobs(t, plan->jobs, mma_w4, &d.mma_chunk_k, &d.mma_n_chunks, &d.n_jobs)) d.jobs_host = &plan->jobs;
+  d.n_mma_w4 = static_cast<int>(mma_w4.size());
   auto pow_table = [](float a) {
     std::vector<float2> tab(256);
     for (int e = 0; e < 256; ++e) {
@@ -844,6 +884,15 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
     stats[2] = static_cast<double>(host_stats[2]) / 65536.0;
   }
   return AC_OK;
+}
+
+// ------------------------------------------------------------------------------------- bitstream statistics
+int ac_codec_stats_i32(const int32_t* q, int64_t n, uint64_t* stats_dev, void* stream) {
+  if (n < 0) return fail(AC_ERR_INVALID, "negative size");
+  if (stats_dev == nullptr || (n > 0 && q == nullptr)) return fail(AC_ERR_INVALID, "null tensor");
+  static_assert(sizeof(unsigned long long) == sizeof(uint64_t), "64-bit counters");
+  cudaError_t err = ac::codec_stats(q, n, reinterpret_cast<unsigned long long*>(stats_dev), static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "codec_stats launch");
 }
 
 // ------------------------------------------------------------------------------------ float64 compute dtype

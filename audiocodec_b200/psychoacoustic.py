@@ -197,3 +197,32 @@ class PsychoacousticModel:
                                                thr.data_ptr() if thr is not None else None, q.data_ptr(), b, m, c,
                                                stream_ptr(a.device)))
     return (q, thr) if return_threshold else q
+
+  # ---- bitstream statistics and rate loop (no reference symbol) ---------------
+  def bit_estimate(self, q):
+    """{coefficients, nonzero, bits}: bits = sum log2(2|q| + 1), accumulated on the device in 16.16 fixed point."""
+    q, _ = adopt(q, "q", dtype=torch.int32)
+    stats = torch.zeros(3, dtype=torch.int64, device=q.device)
+    with torch.cuda.device(q.device):
+      _capi.check(_capi.lib().ac_codec_stats_i32(q.data_ptr(), q.numel(), stats.data_ptr(), stream_ptr(q.device)))
+    n, nonzero, bits = (int(v) for v in stats.cpu())
+    return {"coefficients": n, "nonzero": nonzero, "bits": bits / 65536.0}
+
+  def encode_at_bitrate(self, mdct_amplitudes, bits_per_coefficient, drown=0.0, iterations=14):
+    """Rate loop: the quantiser step is the masking threshold times ONE scalar (SURVEY.md 8a row Q, "fixed bitrate");
+    the scalar is found by bisection on log2(scale) so that the bit estimate meets the target from below.
+
+    :return: (q, step, thr_scale); bit_estimate(q)["bits"] <= bits_per_coefficient * q.numel()
+    """
+    target = float(bits_per_coefficient) * mdct_amplitudes.numel()
+    lo, hi = -10.0, 10.0                      # log2(scale): bits fall monotonically as the scale grows
+    for _ in range(int(iterations)):
+      mid = 0.5 * (lo + hi)
+      q = self.encode(mdct_amplitudes, drown=drown, thr_scale=2.0 ** mid, return_threshold=False)
+      if self.bit_estimate(q)["bits"] > target:
+        lo = mid
+      else:
+        hi = mid
+    scale = 2.0 ** hi
+    q, step = self.encode(mdct_amplitudes, drown=drown, thr_scale=scale)
+    return q, step, scale

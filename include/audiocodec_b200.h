@@ -69,6 +69,16 @@ int ac_mdct_tables_host(int filters_n, int window_type, int precompute_f32, doub
 int ac_pa_tables_host(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha,
                       float* W, float* W_inv, float* quiet, float* spreading, double* scalars);
 
+/* Host-side job list of the tensor-core masking kernel (no CUDA needed; for tests and tooling): the filter axis in
+ * chunks of counts[0] filters; jobs[4j..4j+3] = { byte offset of the first row of the chunk buffer (264 bytes per
+ * filter), byte offset of the job's zero-padded weights (each stored twice), steps of four filters, byte offset of
+ * the band's row of P (256 bytes per band, swizzle folded in) | starts-in-an-earlier-chunk << 16 | band-complete << 17 };
+ * job_start[9c + w] .. job_start[9c + w + 1]: jobs of warp w in chunk c; ton_start likewise for the filters of the
+ * tonality pass; weights[counts[3]]; counts = { chunk, chunks, jobs, weights, fits-the-kernel-parameter }.
+ * Arrays may be NULL; size them for 112 jobs and 32 chunks. */
+int ac_pa_mma_jobs_host(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha, int32_t* jobs,
+                        int32_t* job_start, int16_t* ton_start, float* weights, int32_t* counts);
+
 /* ------------------------------------------------------------------------------------------- MDCT */
 /* MDCTransformer.__init__ (mdctransformer.py:13-59).  filters_n must be even (AC_ERR_INVALID otherwise,
  * the reference asserts at :26).  Tables go to the current device. */
@@ -117,6 +127,12 @@ int ac_pa_add_noise_f32(const float* y, const float* thr, float* out, int64_t n,
  * q = rint(y / thr) with IEEE division and round-half-even;  y_hat = q * thr. */
 int ac_quantize_f32(const float* y, const float* thr, int32_t* q, int64_t n, void* stream);
 int ac_dequantize_f32(const int32_t* q, const float* thr, float* y, int64_t n, void* stream);
+
+/* Bitstream statistics of a tensor of quantised integers (the quantities gathered across ranks at the end of a job,
+ * SURVEY.md 8e; no reference symbol): stats_dev[0..2] += { n, non-zero integers, sum log2(2|q|+1) in 16.16 fixed
+ * point }.  stats_dev is DEVICE memory (three 64-bit counters the caller zeroes); integer accumulation, so the
+ * result does not depend on the order of the atomics.  Basis of the rate loop in the Python layer. */
+int ac_codec_stats_i32(const int32_t* q, int64_t n, uint64_t* stats_dev, void* stream);
 
 /* ------------------------------------------------------------------------- float64 compute dtype */
 /* The reference accepts compute_dtype=tf.float64 for both classes (mdctransformer.py:13-23,

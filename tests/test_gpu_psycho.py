@@ -297,3 +297,25 @@ def test_non_finite_amplitudes_stay_local():
         if keep[b, f, ch]:
           assert np.array_equal(step[b, f, :, ch], step_ref[b, f, :, ch])
           assert np.array_equal(q[b, f, :, ch], q_ref[b, f, :, ch])
+
+
+def test_bit_estimate_and_rate_loop():
+  """Device-side bitstream statistics equal the definition; the rate loop meets its target from below."""
+  sr, n, c = 44100, 256, 2
+  x = cuda(oracle.synthetic_audio(4, 40 * n, c, sr))
+  codec = audiocodec_b200.AudioCodec(sr, filters_n=n)
+  pa = codec.psychoacoustic
+  y = codec.mdct.transform(x)
+  q, _ = pa.encode(y)
+  est = pa.bit_estimate(q)
+  qa = q.abs().double()
+  assert est["coefficients"] == q.numel() and est["nonzero"] == int((qa > 0).sum().item())
+  assert abs(est["bits"] - torch.log2(2 * qa + 1).sum().item()) <= 1e-4 * est["bits"]
+  last = None
+  for bpc in (2.0, 1.0, 0.5):
+    qr, step, scale = pa.encode_at_bitrate(y, bpc)
+    bits = pa.bit_estimate(qr)["bits"]
+    assert bits <= bpc * q.numel() and bits >= 0.98 * bpc * q.numel()
+    assert torch.equal(qr, pa.quantize(y, step))
+    assert last is None or scale > last          # fewer bits need a coarser step
+    last = scale

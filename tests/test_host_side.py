@@ -132,3 +132,50 @@ def test_pa_mma_index_maps_emulation():
   mod = importlib.util.module_from_spec(spec)
   spec.loader.exec_module(mod)
   mod.main()
+
+
+@pytest.mark.parametrize("sr,n", [(44100, 256), (48000, 1024), (44100, 320), (22050, 512), (44100, 64), (48000, 2048)])
+def test_mma_job_list_reproduces_w(sr, n):
+  """The job list of the tensor-core masking kernel (ac_pa_mma_jobs_host) is a lossless re-arrangement of W: every
+  non-zero W[k][band] appears exactly once at the right chunk row, flags mark bands that cross chunks, the warps'
+  job ranges and tonality ranges tile each chunk."""
+  import ctypes
+  from audiocodec_b200 import _capi
+  nb = 64
+  jobs = np.zeros(4 * 112, dtype=np.int32)
+  start = np.zeros(9 * 32 + 1, dtype=np.int32)
+  ton = np.zeros(9 * 32 + 2, dtype=np.int16)
+  weights = np.zeros(8 * (n + 4 * nb), dtype=np.float32)
+  counts = np.zeros(5, dtype=np.int32)
+  _capi.check(_capi.lib().ac_pa_mma_jobs_host(float(sr), n, nb, 0.6, jobs.ctypes.data, start.ctypes.data, ton.ctypes.data,
+                                              weights.ctypes.data, counts.ctypes.data))
+  chunk, n_chunks, n_jobs, n_w, fits = (int(v) for v in counts)
+  assert fits == 1 and chunk == 64 and n_chunks == (n + 63) // 64 and n_w % 4 == 0
+  w = np.empty((n, nb), dtype=np.float32)
+  fp = ctypes.POINTER(ctypes.c_float)
+  _capi.check(_capi.lib().ac_pa_tables_host(float(sr), n, nb, 0.6, w.ctypes.data_as(fp), None, None, None, None))
+  rec = np.zeros_like(w)
+  seen_band = set()
+  for c in range(n_chunks):
+    kc0, kcn = c * chunk, min(chunk, n - c * chunk)
+    assert start[9 * c] <= start[9 * c + 8] and list(start[9 * c:9 * c + 9]) == sorted(start[9 * c:9 * c + 9])
+    if c + 1 < n_chunks:
+      assert start[9 * c + 8] == start[9 * (c + 1)]
+    t = ton[9 * c:9 * c + 9]
+    assert t[0] == 0 and t[8] == kcn and list(t) == sorted(t)
+    for j in range(start[9 * c], start[9 * c + 8]):
+      x, y, steps, wd = (int(v) for v in jobs[4 * j:4 * j + 4])
+      band, swz = (wd & 0xffff) // 256, ((wd & 0xffff) % 256) // 4
+      assert swz == (band & 3) << 3 and x % 264 == 0 and y % 32 == 0 and steps >= 1
+      row0 = x // 264
+      assert row0 + 4 * steps <= kcn + 3                       # padded steps stay inside the three zero rows
+      assert bool(wd & 0x10000) == (band in seen_band)         # an earlier chunk holds the first part of the band
+      for s in range(4 * steps):
+        wt = weights[y // 8 + s]
+        if wt != 0.0:
+          assert row0 + s < kcn and rec[kc0 + row0 + s, band] == 0.0
+          rec[kc0 + row0 + s, band] = wt
+      nz = np.nonzero(w[:, band])[0]
+      assert bool(wd & 0x20000) == (nz[-1] < kc0 + kcn)        # complete when its last filter is in this chunk
+      seen_band.add(band)
+  assert start[9 * n_chunks] == n_jobs and np.array_equal(rec, w)
