@@ -93,10 +93,9 @@ class AudioCodec:
   def __del__(self):
     self._drop_pipes()
 
-  @staticmethod
-  def stats(q):
-    """Per-shard bitstream statistics gathered across ranks at the end of a job."""
-    qa = q.abs().to(torch.float32)
-    return torch.stack([torch.tensor(float(q.numel()), device=q.device),
-                        (qa > 0).sum().to(torch.float32),
-                        torch.log2(2.0 * qa + 1.0).sum()])
+  def stats(self, q):
+    """Per-shard bitstream statistics gathered across ranks at the end of a job: a device tensor
+    [coefficients, non-zero integers, sum log2(2|q|+1)], counted by the library's own kernel (ac_codec_stats_i32)."""
+    est = self.psychoacoustic.bit_estimate(q)
+    return torch.tensor([float(est["coefficients"]), float(est["nonzero"]), est["bits"]], dtype=torch.float64,
+                        device=q.device)
