@@ -3,23 +3,32 @@
 //
 // Reference behaviour: /root/reference/audiocodec/psychoacoustic.py:102-120 (tonality), :122-148
 // (global_masking_threshold), :169-210 (_masking_intensity_in_bark), :301-331 (bark mappings); quantiser = SURVEY.md
-// 8a row Q.  Same mathematics as pa_tile_kernel (psycho_kernels.cu), restructured around its instruction budget:
+// 8a row Q.  Same mathematics as pa_tile_kernel (psycho_kernels.cu), restructured around its instruction budget.
+// An 8-warp CTA (three per SM) walks tiles of 64 (frame, channel) items; the filter axis goes through shared memory in
+// chunks of 64 filters, two chunk buffers (one lands while the other is read):
 //
-//   A1  lane <-> filter k   coalesced read of y, I = y^2 written TRANSPOSED to T[k][item], tonality sums
-//   A2  lane <-> item       one job per (bark band, chunk): steps of four filters, then P = max(eps, I_bark)^alpha
-//                           through an exponent table (x^a = 2^(a lg2 mantissa + r[E]) * 2^n[E]: no int <-> float
-//                           conversions, the exponent keeps fp32 precision), P stored XOR-swizzled
+//   load  cp.async          y[frame][k][c] -> T[k][item] by 8-byte (two channels) asynchronous copies: the copy itself
+//                           transposes; chunk c + 1 (or chunk 0 of the next tile) is in flight while chunk c is used
+//   A1  lane <-> item pair  tonality sums over the chunk (packed fp32, two filters per logarithm); the chunk's filters are
+//                           dealt to the warps so that they level the band-sum jobs (PaJobParams::ton_start)
+//   A2  lane <-> item pair  one job per (bark band, chunk): steps of four filters (LDS.64, square, FFMA2 per filter and
+//                           item pair); the job list is a by-value kernel parameter = constant bank = warp-uniform
+//                           control; P = max(eps, I_bark)^alpha through an exponent table (x^a = 2^(a lg2 mantissa +
+//                           r[E]) * 2^n[E]: no int <-> float conversions, the exponent keeps fp32 precision), P stored
+//                           XOR-swizzled
 //   B   mma.sync m16n8k8    acc[item][j] = sum_i P[item][i] S[i][j] as an error-compensated TF32 product
 //                           (P = hi + lo, S = hi + lo, three MMAs: lo hi + hi lo + hi hi; every term is positive, the
-//                           dropped lo lo term is 2^-22 relative) with fp32 accumulators: 32 items x 32 bands per warp.
+//                           dropped lo lo term is 2^-22 relative) with fp32 accumulators: 16 items x 32 bands per warp.
 //                           The Toeplitz S is read from two 128-entry tables; fragment (k-step, n-tile) only depends
 //                           on n-tile - k-step, so one new fragment per k-step is loaded and the rest rotate.
 //       epilogue            in the accumulator layout: the masking offset joins the exponent of ^(1/alpha)
 //                           (10^(-alpha offset / 10))^(1/alpha) = 2^(offset_log2 offset)), quiet threshold, scale^2
 //   D   lane <-> filter k   thr = sqrt(sum_b G[b] W_inv[b][k]) as v * rsqrt(v); the same rsqrt seeds the division
-//                           q = rint(y / thr) (two exact-residual corrections: the IEEE quotient), coalesced stores
+//                           q = rint(y / thr) (two exact-residual corrections: the IEEE quotient), whole rows per warp,
+//                           the re-read of y (an L2 hit) issued 256 filters ahead
 //
-// y is read from HBM in A1 and again (an L2 hit) in D: HBM sees one read of y and one write each of thr and q.
+// y is read from HBM by the copies and again (an L2 hit) in D: HBM sees one read of y and one write each of thr and q.
+// tools/emulate_pa_mma.py checks the fragment / swizzle index maps on the CPU; profiles/README.md has the measurements.
 #include "kernels.h"
 
 #include <algorithm>
