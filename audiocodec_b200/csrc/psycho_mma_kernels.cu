@@ -346,6 +346,59 @@ __device__ __forceinline__ void phase_d_unit(const float4* __restrict__ filt4, c
   }
 }
 
+// Mono: TWO consecutive frame rows per call - items (2p, 2p + 1) are adjacent in G, so the pair runs on the packed
+// fp32 path of the stereo code (half the arithmetic instructions of two scalar rows); y / thr / q of the two rows are
+// separate 4-byte accesses.  row_b: the second row exists (the last row of a ragged tile may be alone).
+template <bool QUANT, bool THR, bool FILT_SMEM, int KI>
+__device__ __forceinline__ void phase_d_unit_mono2(const float4* __restrict__ filt4, const unsigned masks,
+                                                   const float (&ya)[KI], const float (&yb)[KI], float* __restrict__ ta,
+                                                   float* __restrict__ tb_, int32_t* __restrict__ qa,
+                                                   int32_t* __restrict__ qb, const float* gr, const float eps_s2,
+                                                   const bool row_b) {
+  constexpr int GS = kGS;
+  const u64 k_neg = pack2(-1.f, -1.f);
+#pragma unroll
+  for (int i = 0; i < KI; ++i) {
+    const float4 f4i = FILT_SMEM ? filt4[32 * i] : __ldg(filt4 + 32 * i);
+    const float* gp = gr + __float_as_int(f4i.w) * GS;
+    const unsigned m = masks >> (3 * i);
+    u64 v2;                                    // warp-uniform branch on the slot pattern of the 32-filter group
+    if ((m & 7u) == 3u) {
+      v2 = ffma2(*reinterpret_cast<const u64*>(gp + GS), pack2(f4i.y, f4i.y),
+                 fmul2(*reinterpret_cast<const u64*>(gp), pack2(f4i.x, f4i.x)));
+    } else if ((m & 7u) == 6u) {
+      v2 = ffma2(*reinterpret_cast<const u64*>(gp + 2 * GS), pack2(f4i.z, f4i.z),
+                 fmul2(*reinterpret_cast<const u64*>(gp + GS), pack2(f4i.y, f4i.y)));
+    } else {
+      v2 = ffma2(*reinterpret_cast<const u64*>(gp + 2 * GS), pack2(f4i.z, f4i.z),
+                 ffma2(*reinterpret_cast<const u64*>(gp + GS), pack2(f4i.y, f4i.y),
+                       fmul2(*reinterpret_cast<const u64*>(gp), pack2(f4i.x, f4i.x))));
+    }
+    float vx, vy;
+    unpack2(v2, vx, vy);
+    vx = fmaxf(eps_s2, vx);
+    vy = fmaxf(eps_s2, vy);
+    const u64 r2 = pack2(rsqrt_approx(vx), rsqrt_approx(vy));
+    const u64 th2 = fmul2(pack2(vx, vy), r2);
+    float tx, ty;
+    unpack2(th2, tx, ty);
+    if (QUANT) {
+      const u64 nd = fmul2(th2, k_neg), a2 = pack2(ya[i], yb[i]);
+      u64 qq = fmul2(a2, r2);
+      qq = ffma2(ffma2(nd, qq, a2), r2, qq);
+      qq = ffma2(ffma2(nd, qq, a2), r2, qq);
+      float qx, qy;
+      unpack2(qq, qx, qy);
+      __stcs(qa + 32 * i, __float2int_rn(qx));          // streaming: keep y in L2, not q
+      if (row_b) __stcs(qb + 32 * i, __float2int_rn(qy));
+    }
+    if (THR) {
+      __stcs(ta + 32 * i, tx);
+      if (row_b) __stcs(tb_ + 32 * i, ty);
+    }
+  }
+}
+
 template <int C, bool QUANT, int NFIX>
 __global__ void __launch_bounds__(kThreads, 3)
 pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_constant__ PaJobParams jp,
@@ -712,7 +765,43 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       const bool thr = thr_out != nullptr;
       constexpr int KI = C == 4 ? 4 : 8;
       const int rows_live = (ablate & 16) ? 0 : min(ROWS, nf - warp * ROWS);
-      if (n % (32 * KI) == 0) {
+      if (C == 1 && n % (32 * KI) == 0) {
+        // mono: pairs of consecutive rows on the packed path (phase_d_unit_mono2)
+        if constexpr (C == 1) {
+          const int upr = n / (32 * KI);
+#pragma unroll 1
+          for (int r = 0; r < rows_live; r += 2) {
+            const bool row_b = r + 1 < rows_live;
+            const int64_t offa = ((f0 + warp * ROWS + r) * static_cast<int64_t>(n) + lane);
+            const int64_t offb = row_b ? offa + n : offa;          // a lone last row is read twice, stored once
+            const float* gr = G + warp * ROWS + r;
+#pragma unroll 1
+            for (int u = 0; u < upr; ++u) {
+              const int k0 = u * (32 * KI);
+              float ya[KI], yb[KI];
+              if (QUANT) {
+#pragma unroll
+                for (int i = 0; i < KI; ++i) {
+                  ya[i] = __ldg(y + offa + k0 + 32 * i);
+                  yb[i] = __ldg(y + offb + k0 + 32 * i);
+                }
+              }
+              unsigned masks = 0;
+#pragma unroll
+              for (int i = 0; i < KI; ++i) masks |= static_cast<unsigned>(tb.filt_mask[k0 / 32 + i]) << (3 * i);
+#define AC_PHASE_D(THR_, FS_)                                                                                       \
+  phase_d_unit_mono2<QUANT, THR_, FS_, KI>((FS_ ? s_filt4 : tb.filt4) + k0 + lane, masks, ya, yb, thr_out + offa + k0, \
+                                           thr_out + offb + k0, q_out + offa + k0, q_out + offb + k0, gr, eps_s2, row_b)
+              if (filt_smem) {
+                if (thr) AC_PHASE_D(true, true); else AC_PHASE_D(false, true);
+              } else {
+                if (thr) AC_PHASE_D(true, false); else AC_PHASE_D(false, false);
+              }
+#undef AC_PHASE_D
+            }
+          }
+        }
+      } else if (n % (32 * KI) == 0) {
         // the rows of a warp are contiguous in memory: its units are one flat sequence; the y values of unit u + 1
         // are loaded (an L2 hit) before unit u is computed
         const int upr = n / (32 * KI);          // units per row
