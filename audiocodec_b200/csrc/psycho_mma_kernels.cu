@@ -399,6 +399,78 @@ __device__ __forceinline__ void phase_d_unit_mono2(const float4* __restrict__ fi
   }
 }
 
+// R item PAIRS per call (stereo: the two channels of R consecutive frame rows; mono: R pairs of consecutive rows) share
+// the filter-table entry, the slot-pattern branch and the address of the band rows of G (pair h's items sit 2 h floats
+// further), and their dependency chains interleave: fewer shared-memory wavefronts and control instructions per
+// coefficient than one pair at a time.  row_stride in floats; yv[h][i] = the pair's two amplitudes of filter 32 i + lane.
+template <int C, bool QUANT, bool THR, bool FILT_SMEM, int KI, int R>
+__device__ __forceinline__ void phase_d_unit_pairs(const float4* __restrict__ filt4, const unsigned masks,
+                                                    const float2 (&yv)[R][KI], float* __restrict__ t0,
+                                                    int32_t* __restrict__ q0, const size_t row_stride, const float* gr,
+                                                    const float eps_s2) {
+  constexpr int GS = kGS;
+  const u64 k_neg = pack2(-1.f, -1.f);
+#pragma unroll
+  for (int i = 0; i < KI; ++i) {
+    const float4 f4i = FILT_SMEM ? filt4[32 * i] : __ldg(filt4 + 32 * i);
+    const float* gp = gr + __float_as_int(f4i.w) * GS;
+    const unsigned m = masks >> (3 * i);
+    u64 v[R];                                  // warp-uniform branch on the slot pattern of the 32-filter group
+    if ((m & 7u) == 3u) {
+      const u64 w0 = pack2(f4i.x, f4i.x), w1 = pack2(f4i.y, f4i.y);
+#pragma unroll
+      for (int h = 0; h < R; ++h)
+        v[h] = ffma2(*reinterpret_cast<const u64*>(gp + GS + 2 * h), w1, fmul2(*reinterpret_cast<const u64*>(gp + 2 * h), w0));
+    } else if ((m & 7u) == 6u) {
+      const u64 w1 = pack2(f4i.y, f4i.y), w2 = pack2(f4i.z, f4i.z);
+#pragma unroll
+      for (int h = 0; h < R; ++h)
+        v[h] = ffma2(*reinterpret_cast<const u64*>(gp + 2 * GS + 2 * h), w2,
+                     fmul2(*reinterpret_cast<const u64*>(gp + GS + 2 * h), w1));
+    } else {
+      const u64 w0 = pack2(f4i.x, f4i.x), w1 = pack2(f4i.y, f4i.y), w2 = pack2(f4i.z, f4i.z);
+#pragma unroll
+      for (int h = 0; h < R; ++h)
+        v[h] = ffma2(*reinterpret_cast<const u64*>(gp + 2 * GS + 2 * h), w2,
+                     ffma2(*reinterpret_cast<const u64*>(gp + GS + 2 * h), w1,
+                           fmul2(*reinterpret_cast<const u64*>(gp + 2 * h), w0)));
+    }
+#pragma unroll
+    for (int h = 0; h < R; ++h) {
+      float vx, vy;
+      unpack2(v[h], vx, vy);
+      vx = fmaxf(eps_s2, vx);
+      vy = fmaxf(eps_s2, vy);
+      const u64 r2 = pack2(rsqrt_approx(vx), rsqrt_approx(vy));
+      const u64 th2 = fmul2(pack2(vx, vy), r2);
+      if (QUANT) {
+        const u64 nd = fmul2(th2, k_neg), a2 = pack2(yv[h][i].x, yv[h][i].y);
+        u64 qq = fmul2(a2, r2);
+        qq = ffma2(ffma2(nd, qq, a2), r2, qq);
+        qq = ffma2(ffma2(nd, qq, a2), r2, qq);
+        float qx, qy;
+        unpack2(qq, qx, qy);
+        if constexpr (C == 2) {
+          __stcs(reinterpret_cast<int2*>(q0 + h * row_stride) + 32 * i, make_int2(__float2int_rn(qx), __float2int_rn(qy)));
+        } else {
+          __stcs(q0 + (2 * h) * row_stride + 32 * i, __float2int_rn(qx));
+          __stcs(q0 + (2 * h + 1) * row_stride + 32 * i, __float2int_rn(qy));
+        }
+      }
+      if (THR) {                                // streaming stores: keep y in L2, not thr / q
+        if constexpr (C == 2) {
+          __stcs(reinterpret_cast<u64*>(t0 + h * row_stride) + 32 * i, th2);
+        } else {
+          float tx, ty;
+          unpack2(th2, tx, ty);
+          __stcs(t0 + (2 * h) * row_stride + 32 * i, tx);
+          __stcs(t0 + (2 * h + 1) * row_stride + 32 * i, ty);
+        }
+      }
+    }
+  }
+}
+
 template <int C, bool QUANT, int NFIX>
 __global__ void __launch_bounds__(kThreads, 3)
 pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_constant__ PaJobParams jp,
@@ -765,7 +837,8 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       const bool thr = thr_out != nullptr;
       constexpr int KI = C == 4 ? 4 : 8;
       const int rows_live = (ablate & 16) ? 0 : min(ROWS, nf - warp * ROWS);
-      if (C == 1 && n % (32 * KI) == 0) {
+      const bool whole = C <= 2 && n % 64 == 0 && rows_live == ROWS && filt_smem;   // the common case, see below
+      if (C == 1 && n % (32 * KI) == 0 && !whole) {
         // mono: pairs of consecutive rows on the packed path (phase_d_unit_mono2)
         if constexpr (C == 1) {
           const int upr = n / (32 * KI);
@@ -798,6 +871,43 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
                 if (thr) AC_PHASE_D(true, false); else AC_PHASE_D(false, false);
               }
 #undef AC_PHASE_D
+            }
+          }
+        }
+      } else if (whole) {
+        // whole tile, stereo / mono: the warp's four item pairs together (stereo: its four rows; mono: four of its eight
+        // rows, as pairs), 64 filters at a time (phase_d_unit_pairs); measured against 2 pairs x 64 / 128 / 256 filters
+        // and 4 pairs x 32 / 128 filters (profiles/README.md)
+        if constexpr (C <= 2) {
+          constexpr int R = 4, K2 = 2;
+          const size_t rs = static_cast<size_t>(n) * C;
+          const int upr = n / (32 * K2);
+#pragma unroll 1
+          for (int r0 = 0; r0 < ROWS; r0 += R * (2 / C)) {          // stereo: all four rows at once; mono: rows 0-3, 4-7... in pairs
+            const int64_t off0 = ((f0 + warp * ROWS + r0) * static_cast<int64_t>(n) + lane) * C;
+            const float* gr = G + (warp * ROWS + r0) * C;
+#pragma unroll 1
+            for (int u = 0; u < upr; ++u) {
+              const int k0 = u * (32 * K2);
+              const int64_t off = off0 + C * k0;
+              float2 yv[R][K2];
+              if (QUANT) {                      // an L2 hit; loading a unit ahead changes nothing (measured)
+#pragma unroll
+                for (int h = 0; h < R; ++h)
+#pragma unroll
+                  for (int i = 0; i < K2; ++i) {
+                    if constexpr (C == 2) {
+                      yv[h][i] = __ldg(reinterpret_cast<const float2*>(y + off + h * rs) + 32 * i);
+                    } else {
+                      yv[h][i] = make_float2(__ldg(y + off + (2 * h) * rs + 32 * i), __ldg(y + off + (2 * h + 1) * rs + 32 * i));
+                    }
+                  }
+              }
+              unsigned masks = 0;
+#pragma unroll
+              for (int i = 0; i < K2; ++i) masks |= static_cast<unsigned>(tb.filt_mask[k0 / 32 + i]) << (3 * i);
+              if (thr) phase_d_unit_pairs<C, QUANT, true, true, K2, R>(s_filt4 + k0 + lane, masks, yv, thr_out + off, q_out + off, rs, gr, eps_s2);
+              else     phase_d_unit_pairs<C, QUANT, false, true, K2, R>(s_filt4 + k0 + lane, masks, yv, thr_out + off, q_out + off, rs, gr, eps_s2);
             }
           }
         }
