@@ -837,7 +837,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       const bool thr = thr_out != nullptr;
       constexpr int KI = C == 4 ? 4 : 8;
       const int rows_live = (ablate & 16) ? 0 : min(ROWS, nf - warp * ROWS);
-      const bool whole = C <= 2 && n % 64 == 0 && rows_live == ROWS && filt_smem;   // the common case, see below
+      const bool whole = C <= 2 && n % 64 == 0 && rows_live == ROWS;   // the common case, see below
       if (C == 1 && n % (32 * KI) == 0 && !whole) {
         // mono: pairs of consecutive rows on the packed path (phase_d_unit_mono2)
         if constexpr (C == 1) {
@@ -906,8 +906,14 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
               unsigned masks = 0;
 #pragma unroll
               for (int i = 0; i < K2; ++i) masks |= static_cast<unsigned>(tb.filt_mask[k0 / 32 + i]) << (3 * i);
-              if (thr) phase_d_unit_pairs<C, QUANT, true, true, K2, R>(s_filt4 + k0 + lane, masks, yv, thr_out + off, q_out + off, rs, gr, eps_s2);
-              else     phase_d_unit_pairs<C, QUANT, false, true, K2, R>(s_filt4 + k0 + lane, masks, yv, thr_out + off, q_out + off, rs, gr, eps_s2);
+#define AC_PHASE_D(THR_, FS_) \
+  phase_d_unit_pairs<C, QUANT, THR_, FS_, K2, R>((FS_ ? s_filt4 : tb.filt4) + k0 + lane, masks, yv, thr_out + off, q_out + off, rs, gr, eps_s2)
+              if (filt_smem) {
+                if (thr) AC_PHASE_D(true, true); else AC_PHASE_D(false, true);
+              } else {
+                if (thr) AC_PHASE_D(true, false); else AC_PHASE_D(false, false);
+              }
+#undef AC_PHASE_D
             }
           }
         }
