@@ -506,27 +506,50 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);        // the same value, known to be warp-uniform
   const float scale = QUANT ? thr_scale : 1.0f;
   const float scale2 = scale * scale;
-  for (int i = tid; i < 256; i += kThreads) {
-    s_powa[i] = tb.pow_alpha[i];
-    s_powia[i] = tb.pow_inv_alpha[i];
+  {
+    // the tables: every global load of a thread is issued before its first shared-memory store (one round trip to L2
+    // instead of one per table); kThreads == 256 == entries of the exponent tables
+    static_assert(kThreads == 256, "one exponent-table entry per thread");
+    const float2 pa = tb.pow_alpha[tid], pia = tb.pow_inv_alpha[tid];
+    const float sfv = tb.spread_fn[tid & 127];
+    const float qv = tb.quiet[tid & (kNB - 1)], lv = tb.lin[tid & (kNB - 1)];
+    const int nw = tb.n_mma_w4;
+    float wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) wv[u] = tid + u * kThreads < nw ? tb.mma_w4[tid + u * kThreads] : 0.f;
+    float4 fv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      fv[u] = filt_smem && tid + u * kThreads < n ? tb.filt4[tid + u * kThreads] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s_powa[tid] = pa;
+    s_powia[tid] = pia;
+    if (tid < 128) {
+      uint32_t hi, lo;
+      split_tf32(sfv, hi, lo);
+      s_sfh[tid] = hi;
+      s_sfl[tid] = lo;
+    }
+    if (tid < kNB) {
+      s_quiet[tid] = qv * scale2;
+      s_lin[tid] = lv;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (tid + u * kThreads < nw) {
+        s_bw8[2 * (tid + u * kThreads)] = wv[u];
+        s_bw8[2 * (tid + u * kThreads) + 1] = wv[u];
+      }
+    for (int i = tid + 4 * kThreads; i < nw; i += kThreads) {      // long weight lists (large filters_n)
+      const float w = tb.mma_w4[i];
+      s_bw8[2 * i] = w;
+      s_bw8[2 * i + 1] = w;
+    }
+    if (filt_smem) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (tid + u * kThreads < n) s_filt4[tid + u * kThreads] = fv[u];
+    }
   }
-  for (int i = tid; i < 128; i += kThreads) {
-    uint32_t hi, lo;
-    split_tf32(tb.spread_fn[i], hi, lo);
-    s_sfh[i] = hi;
-    s_sfl[i] = lo;
-  }
-  for (int i = tid; i < kNB; i += kThreads) {
-    s_quiet[i] = tb.quiet[i] * scale2;
-    s_lin[i] = tb.lin[i];
-  }
-  for (int i = tid; i < tb.n_mma_w4; i += kThreads) {
-    const float w = tb.mma_w4[i];
-    s_bw8[2 * i] = w;
-    s_bw8[2 * i + 1] = w;
-  }
-  if (filt_smem)
-    for (int i = tid; i < n; i += kThreads) s_filt4[i] = tb.filt4[i];
 
   const uint32_t sm_base = static_cast<uint32_t>(__cvta_generic_to_shared(sm));
   const uint32_t t_base = sm_base + static_cast<uint32_t>(L.t) * 4u;
