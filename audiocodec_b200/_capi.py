@@ -68,7 +68,8 @@ _lib = None
 
 
 def library_path():
-  return _build.lib_path()
+  # AUDIOCODEC_B200_LIB: an alternative build of the same library (A/B runs of kernel variants, tools/)
+  return os.environ.get("AUDIOCODEC_B200_LIB") or _build.lib_path()
 
 
 def lib():
