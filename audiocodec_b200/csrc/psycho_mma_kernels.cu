@@ -24,8 +24,8 @@
 //       epilogue            in the accumulator layout: the masking offset joins the exponent of ^(1/alpha)
 //                           (10^(-alpha offset / 10))^(1/alpha) = 2^(offset_log2 offset)), quiet threshold, scale^2
 //   D   lane <-> filter k   thr = sqrt(sum_b G[b] W_inv[b][k]) as v * rsqrt(v); the same rsqrt seeds the division
-//                           q = rint(y / thr) (two exact-residual corrections: the IEEE quotient), whole rows per warp,
-//                           the re-read of y (an L2 hit) issued 256 filters ahead
+//                           q = rint(y / thr) (two exact-residual corrections: the IEEE quotient); the four item pairs
+//                           of a warp share one unrolled body per 64 filters (table entry, slot pattern, band rows)
 //
 // y is read from HBM by the copies and again (an L2 hit) in D: HBM sees one read of y and one write each of thr and q.
 // tools/emulate_pa_mma.py checks the fragment / swizzle index maps on the CPU; profiles/README.md has the measurements.
@@ -618,8 +618,6 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
 
     u64 ton_i2 = 0ull, ton_l2 = 0ull;           // tonality sums (psychoacoustic.py:113-116) of the item pair of this lane
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
-      const int kc0 = chunk * tb.mma_chunk_k;
-      const int kcn = (n - kc0 < kc ? n - kc0 : kc);          // filters in this chunk
       cp_async_wait_all();
       __syncthreads();                          // the chunk has landed; the other buffer (and G in it) is free
       if (chunk + 1 < n_chunks) {
@@ -753,14 +751,6 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
 
     // ---- B: spreading on the tensor cores                                 (psychoacoustic.py:195-206)
     {
-      // pull the next tile of y towards L2 while this phase only computes
-      const int64_t next0 = (tile - gridDim.x) * FT;
-      if (next0 >= 0) {
-        const int64_t next_floats = (frames_total - next0 < FT ? frames_total - next0 : FT) * static_cast<int64_t>(n) * C;
-        const float* np = y + next0 * static_cast<int64_t>(n) * C;
-        for (int64_t o = static_cast<int64_t>(tid) * 32; o < next_floats; o += kThreads * 32)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(np + o));
-      }
       const int g = lane >> 2, t = lane & 3;
       const int m0 = (warp & 3) * 16, nq = warp >> 2;            // 16 items x 32 maskee bands per warp
       const int col0 = (m0 + g) ^ (t << 3), col1 = (m0 + g + 8) ^ (t << 3);
@@ -920,9 +910,9 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
 #pragma unroll
                   for (int i = 0; i < K2; ++i) {
                     if constexpr (C == 2) {
-                      yv[h][i] = __ldg(reinterpret_cast<const float2*>(y + off + h * rs) + 32 * i);
+                      yv[h][i] = __ldcg(reinterpret_cast<const float2*>(y + off + h * rs) + 32 * i);   // L2 only
                     } else {
-                      yv[h][i] = make_float2(__ldg(y + off + (2 * h) * rs + 32 * i), __ldg(y + off + (2 * h + 1) * rs + 32 * i));
+                      yv[h][i] = make_float2(__ldcg(y + off + (2 * h) * rs + 32 * i), __ldcg(y + off + (2 * h + 1) * rs + 32 * i));
                     }
                   }
               }
