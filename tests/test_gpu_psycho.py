@@ -258,6 +258,35 @@ def test_mma_tile_kernel_against_other_kernels(sr, n, c, b, m, monkeypatch):
   np.testing.assert_allclose(out["mma"][1], 1.5 * out["mma"][2], rtol=2e-6)
 
 
+def test_full_size_encode_cfg2_kernels_agree(monkeypatch):
+  """The bench workload itself (cfg2: 64 stereo clips x 10 s, 220 544 items, every CTA of the persistent grid walks
+  several tiles from the end of the tensor, last tile ragged): the tensor-core kernel, the first-generation tile kernel
+  and the stand-alone quantiser agree on the whole tensor; compared on the device."""
+  sr, n = 44100, 256
+  gen = torch.Generator(device="cuda").manual_seed(2)
+  x = (torch.rand(64, 440832, 2, device="cuda", generator=gen) - 0.5) * \
+      torch.logspace(-4, 0, 64, device="cuda").view(64, 1, 1)
+  y = audiocodec_b200.MDCTransformer(n).transform(x)
+  del x
+  pa = audiocodec_b200.PsychoacousticModel(sr, n)
+  q, step = pa.encode(y)
+  assert torch.isfinite(step).all() and step.min().item() >= 1e-7 * (1 - 1e-6)
+  assert torch.equal(q, pa.quantize(y, step))               # fused division = IEEE division, every coefficient
+  q_again, step_again = pa.encode(y)
+  assert torch.equal(q, q_again) and torch.equal(step, step_again)     # no run-to-run variation (no atomics)
+  monkeypatch.setenv("AC_PA_KERNEL", "fma")
+  q_fma, step_fma = pa.encode(y)
+  monkeypatch.delenv("AC_PA_KERNEL")
+  rel = ((step - step_fma).abs() / step_fma).max().item()
+  assert rel <= 5e-6
+  dq = (q - q_fma).abs()
+  assert dq.max().item() <= 1 and (dq != 0).float().mean().item() <= 1e-3
+  # decode: the reconstruction error of every coefficient is at most half a quantiser step (+ fp32 rounding of y / step
+  # and q * step)
+  err = (pa.dequantize(q, step) - y).abs()
+  assert (err <= 0.5 * step + 2e-7 * y.abs()).all()
+
+
 def test_unaligned_views_take_the_generic_kernel():
   """A 4-byte-aligned view (odd float offset into a larger buffer) must not reach the vectorised tile kernels."""
   n, c = 256, 2
