@@ -684,6 +684,34 @@ int ac_pa_encode_f32(const ac_pa_plan* plan, const float* y, float drown, float 
   return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_encode launch");
 }
 
+int ac_pa_encode_compact_f32(const ac_pa_plan* plan, const float* y, float drown, float thr_scale, float* bark_thr,
+                             int32_t* q, int64_t batches, int64_t blocks, int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (!(thr_scale > 0.f)) return fail(AC_ERR_INVALID, "thr_scale must be positive");
+  if (batches * blocks == 0) return AC_OK;
+  if (y == nullptr || q == nullptr || bark_thr == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::pa_encode_compact(plan->tb, y, drown, thr_scale, bark_thr, q, batches * blocks, channels,
+                                          static_cast<cudaStream_t>(stream));
+  if (err == cudaErrorNotSupported)
+    return fail(AC_ERR_UNSUPPORTED, "compact side information needs bark_bands_n == 64, <= 3 bands per filter, 1/2/4 channels");
+  if (err == cudaErrorMisalignedAddress) return fail(AC_ERR_INVALID, "compact side information needs 16-byte aligned tensors");
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_encode_compact launch");
+}
+
+int ac_pa_expand_threshold_f32(const ac_pa_plan* plan, const float* bark_thr, float thr_scale, float* thr, int64_t batches,
+                               int64_t blocks, int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (!(thr_scale > 0.f)) return fail(AC_ERR_INVALID, "thr_scale must be positive");
+  if (batches * blocks == 0) return AC_OK;
+  if (bark_thr == nullptr || thr == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::pa_expand_threshold(plan->tb, bark_thr, thr_scale, thr, batches * blocks, channels,
+                                            static_cast<cudaStream_t>(stream));
+  if (err == cudaErrorNotSupported)
+    return fail(AC_ERR_UNSUPPORTED, "compact side information needs bark_bands_n == 64, <= 3 bands per filter, 1/2/4 channels");
+  if (err == cudaErrorMisalignedAddress) return fail(AC_ERR_INVALID, "compact side information needs 16-byte aligned tensors");
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_expand_threshold launch");
+}
+
 int ac_pa_add_noise_f32(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, void* stream) {
   if (n < 0) return fail(AC_ERR_INVALID, "negative size");
   if (n == 0) return AC_OK;

@@ -102,6 +102,9 @@ struct PaDeviceTables {
   const float2* pow_alpha = nullptr;
   const float2* pow_inv_alpha = nullptr;
   float offset_log2 = 0.f;  // fp32(-log2(10) / 10) = gain_log2 / alpha: the masking offset in the log2 domain after ^(1/alpha)
+  // compact side information: when set, the tensor-core tile kernel also writes the bark-domain
+  // thresholds G [rows][channels][64] (intensity, thr_scale^2 folded in) from which pa_expand_threshold rebuilds thr
+  float* bark_out = nullptr;
 };
 
 // psycho_mma_kernels.cu: nb == 64, <= 3 bands per filter, 1 / 2 / 4 channels
@@ -172,5 +175,13 @@ cudaError_t dequantize(const int32_t* q, const float* thr, float* y, int64_t n, 
 // stats[0..2] += { n, non-zero integers, sum of log2(2|q|+1) in 16.16 fixed point }
 cudaError_t codec_stats(const int32_t* q, int64_t n, unsigned long long* stats, cudaStream_t stream);
 cudaError_t add_noise(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, cudaStream_t stream);
+
+// compact side information: q and G [rows][channels][64] instead of q and thr [rows][N][channels]; only on the
+// tensor-core tile kernel (cudaErrorNotSupported otherwise).  pa_expand_threshold: thr = sqrt(G W_inv), the same
+// operations in the same order as phase D of the tile kernel (bit-identical step sizes in encoder and decoder).
+cudaError_t pa_encode_compact(const PaDeviceTables& tb, const float* y, float drown, float thr_scale, float* bark_out,
+                              int32_t* q_out, int64_t rows, int channels, cudaStream_t stream);
+cudaError_t pa_expand_threshold(const PaDeviceTables& tb, const float* bark, float thr_scale, float* thr, int64_t rows,
+                                int channels, cudaStream_t stream);
 
 }  // namespace ac

@@ -843,6 +843,17 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     }
     __syncthreads();
 
+    // compact side information: the tile's bark-domain thresholds G[band][item] -> bark_out[item][band]
+    if (tb.bark_out != nullptr) {
+      const int items_live = nf * C;
+#pragma unroll 1
+      for (int it = warp * (TI / kWarps); it < (warp + 1) * (TI / kWarps) && it < items_live; ++it) {
+        float* go = tb.bark_out + (f0 * C + it) * kNB;
+        go[lane] = G[lane * GS + it];
+        go[lane + 32] = G[(lane + 32) * GS + it];
+      }
+    }
+
     // ---- D: back to the filter bands, amplitude, optional quantiser      (:330-331; quantiser: SURVEY 8a row Q)
     // units of KI x 32 filters: the unit's filter-table entries stay in registers for all rows of the warp; a row
     // of a unit is KI x 32 x C contiguous floats of thr and of q (long DRAM bursts)
@@ -1042,7 +1053,78 @@ cudaError_t launch_mma_tile(const PaDeviceTables& tb, const float* y, const floa
   return launch_mma_tile_q<C, false>(tb, y, ton_in, omd, thr_scale, thr_out, q_out, frames, stream);
 }
 
+// Decoder side of the compact side information: one warp per frame row rebuilds thr[row][k][c] from G[row][c][64].
+// v = G[b] w0 + G[b + 1] w1 + G[b + 2] w2 in the order of phase D (its two-slot patterns are the same sums with a zero
+// weight), the same clamp and the same rsqrt: bit-identical to the thr the encoder quantised with.
+template <int C>
+__global__ void __launch_bounds__(256) pa_expand_threshold_kernel(const float4* __restrict__ filt4,
+                                                                  const float* __restrict__ bark, const float eps_s2,
+                                                                  float* __restrict__ thr, const int64_t rows,
+                                                                  const int n) {
+  __shared__ float s_g[8][C][kNB + 4];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float* g = bark + (row * C + c) * kNB;
+      s_g[warp][c][lane] = __ldcs(g + lane);
+      s_g[warp][c][lane + 32] = __ldcs(g + lane + 32);
+      if (lane < 4) s_g[warp][c][kNB + lane] = 0.f;
+    }
+    __syncwarp();
+    float* out = thr + row * static_cast<int64_t>(n) * C;
+    for (int k = lane; k < n; k += 32) {
+      const float4 f4 = __ldg(filt4 + k);
+      const int b = __float_as_int(f4.w);
+      float t[C];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float* g = &s_g[warp][c][b];
+        const float v = fmaxf(eps_s2, fmaf(g[2], f4.z, fmaf(g[1], f4.y, g[0] * f4.x)));
+        t[c] = v * rsqrt_approx(v);
+      }
+      if constexpr (C == 2) {
+        __stcs(reinterpret_cast<float2*>(out) + k, make_float2(t[0], t[1]));
+      } else if constexpr (C == 4) {
+        __stcs(reinterpret_cast<float4*>(out) + k, make_float4(t[0], t[1], t[2], t[3]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; ++c) __stcs(out + static_cast<int64_t>(k) * C + c, t[c]);
+      }
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t pa_encode_compact(const PaDeviceTables& tb, const float* y, float drown, float thr_scale, float* bark_out,
+                              int32_t* q_out, int64_t rows, int channels, cudaStream_t stream) {
+  if (!pa_mma_tile_supported(tb, channels)) return cudaErrorNotSupported;
+  if ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(q_out) | reinterpret_cast<uintptr_t>(bark_out)) & 15)
+    return cudaErrorMisalignedAddress;
+  PaDeviceTables with_out = tb;
+  with_out.bark_out = bark_out;
+  return pa_threshold_mma_tile(with_out, y, nullptr, static_cast<float>(1.0 - static_cast<double>(drown)), thr_scale, nullptr,
+                               q_out, rows, channels, stream);
+}
+
+cudaError_t pa_expand_threshold(const PaDeviceTables& tb, const float* bark, float thr_scale, float* thr, int64_t rows,
+                                int channels, cudaStream_t stream) {
+  if (tb.nb != kNB || tb.filt4 == nullptr || !tb.tile_ok) return cudaErrorNotSupported;
+  if ((reinterpret_cast<uintptr_t>(thr) | reinterpret_cast<uintptr_t>(bark)) & 15) return cudaErrorMisalignedAddress;
+  const float eps_s2 = tb.eps * (thr_scale * thr_scale);
+  const int64_t want = (rows + 7) / 8;
+  const int grid = static_cast<int>(want < 16LL * tile_sm_count() ? want : 16LL * tile_sm_count());
+  count_launch();
+  switch (channels) {
+    case 1: pa_expand_threshold_kernel<1><<<grid, 256, 0, stream>>>(tb.filt4, bark, eps_s2, thr, rows, tb.n); break;
+    case 2: pa_expand_threshold_kernel<2><<<grid, 256, 0, stream>>>(tb.filt4, bark, eps_s2, thr, rows, tb.n); break;
+    case 4: pa_expand_threshold_kernel<4><<<grid, 256, 0, stream>>>(tb.filt4, bark, eps_s2, thr, rows, tb.n); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
 
 bool pa_mma_tile_supported(const PaDeviceTables& tb, int channels) {
   if (!tb.tile_ok || tb.nb != kNB || tb.jobs_host == nullptr) return false;

@@ -198,6 +198,41 @@ class PsychoacousticModel:
                                                stream_ptr(a.device)))
     return (q, thr) if return_threshold else q
 
+  # ---- compact side information (decoder-side mapping: psychoacoustic.py:330-331) ----
+  def encode_compact(self, mdct_amplitudes, drown=0.0, thr_scale=1.0):
+    """Like encode(), but the side information is the 64 bark-domain thresholds of every (frame, channel) instead of
+    one step per coefficient: N / 64 times fewer floats to store next to q.
+
+    :return: (q int32 [B, M, N, C], bark_thr float32 [B, M, C, 64]); expand_threshold(bark_thr, thr_scale) is
+             bit-identical to the step of encode().
+    """
+    if self._f64:
+      raise NotImplementedError("compact side information is built for float32 only")
+    a, _ = adopt(mdct_amplitudes, "mdct_amplitudes")
+    self._check_amplitudes(a)
+    b, m, _, c = a.shape
+    q = torch.empty(a.shape, dtype=torch.int32, device=a.device)
+    bark = torch.empty((b, m, c, 64), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+      _capi.check(_capi.lib().ac_pa_encode_compact_f32(self._plan(a.device), a.data_ptr(), float(drown), float(thr_scale),
+                                                       bark.data_ptr(), q.data_ptr(), b, m, c, stream_ptr(a.device)))
+    return q, bark
+
+  def expand_threshold(self, bark_thr, thr_scale=1.0):
+    """Decoder side of encode_compact: step [B, M, N, C] = sqrt(bark_thr W_inv) (psychoacoustic.py:330-331). thr_scale
+    must be the encoder's (it only enters through the eps floor of the mapping)."""
+    if self._f64:
+      raise NotImplementedError("compact side information is built for float32 only")
+    g, back = adopt(bark_thr, "bark_thr")
+    if g.dim() != 4 or g.shape[3] != 64:
+      raise ValueError("bark_thr must be [batches, blocks, channels, 64]")
+    b, m, c, _ = g.shape
+    thr = torch.empty((b, m, self.filter_bands_n, c), dtype=torch.float32, device=g.device)
+    with torch.cuda.device(g.device):
+      _capi.check(_capi.lib().ac_pa_expand_threshold_f32(self._plan(g.device), g.data_ptr(), float(thr_scale),
+                                                         thr.data_ptr(), b, m, c, stream_ptr(g.device)))
+    return back(thr)
+
   # ---- bitstream statistics and rate loop (no reference symbol; SURVEY.md 8e / 8f row 4) ---------------
   def bit_estimate(self, q):
     """{coefficients, nonzero, bits}: bits = sum log2(2|q| + 1), accumulated on the device in 16.16 fixed point."""

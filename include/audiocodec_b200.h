@@ -119,6 +119,17 @@ int ac_pa_encode_f32(const ac_pa_plan* plan, const float* y, float drown, float 
                      float* thr_out, int32_t* q,
                      int64_t batches, int64_t blocks, int channels, void* stream);
 
+/* Compact side information (the decoder-side mapping is psychoacoustic.py:330-331): the encoder
+ * writes q and the 64 bark-domain thresholds per (frame, channel) - bark_thr [B, M, C, 64], intensities with
+ * thr_scale^2 folded in - instead of one threshold per coefficient; ac_pa_expand_threshold_f32 rebuilds
+ * step [B, M, N, C] = sqrt(bark_thr W_inv) with the operations of the encoder, bit-identical to the step q was
+ * quantised with.  AC_ERR_UNSUPPORTED unless bark_bands_n == 64 with <= 3 bands per filter and 1/2/4 channels. */
+int ac_pa_encode_compact_f32(const ac_pa_plan* plan, const float* y, float drown, float thr_scale,
+                             float* bark_thr, int32_t* q,
+                             int64_t batches, int64_t blocks, int channels, void* stream);
+int ac_pa_expand_threshold_f32(const ac_pa_plan* plan, const float* bark_thr, float thr_scale, float* thr,
+                               int64_t batches, int64_t blocks, int channels, void* stream);
+
 /* PsychoacousticModel.add_noise (psychoacoustic.py:150-167): out = y + thr * N(0, 1/6), counter-based RNG. */
 int ac_pa_add_noise_f32(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, void* stream);
 

@@ -287,6 +287,37 @@ def test_full_size_encode_cfg2_kernels_agree(monkeypatch):
   assert (err <= 0.5 * step + 2e-7 * y.abs()).all()
 
 
+# ---- compact side information: q + 64 bark-domain thresholds per (frame, channel), SURVEY.md 8f row 2 ------
+@pytest.mark.parametrize("sr,n,c,b,m", [(44100, 256, 2, 3, 37), (44100, 256, 1, 2, 70), (44100, 256, 4, 2, 11),
+                                        (48000, 1024, 2, 2, 19), (44100, 512, 2, 1, 18), (44100, 320, 2, 2, 9),
+                                        (48000, 2048, 1, 1, 5), (44100, 256, 2, 64, 431)])
+def test_compact_side_information_rebuilds_the_step_bit_for_bit(sr, n, c, b, m):
+  rng = np.random.default_rng(3 * n + c)
+  y = cuda((rng.standard_normal((b, m, n, c)) * 10.0 ** rng.uniform(-5, 0, (b, m, 1, c))).astype(np.float32))
+  pa = audiocodec_b200.PsychoacousticModel(sr, n)
+  q, step = pa.encode(y, thr_scale=1.5, drown=0.25)
+  qc, bark = pa.encode_compact(y, thr_scale=1.5, drown=0.25)
+  assert bark.shape == (b, m, c, 64) and torch.isfinite(bark).all() and bark.min().item() > 0
+  assert torch.equal(q, qc)
+  rebuilt = pa.expand_threshold(bark, thr_scale=1.5)
+  assert torch.equal(rebuilt, step)                         # decoder and encoder use the same step, bit for bit
+  assert torch.equal(pa.dequantize(qc, rebuilt), pa.dequantize(q, step))
+
+
+def test_compact_side_information_unsupported_configurations():
+  pa = audiocodec_b200.PsychoacousticModel(44100, 256, bark_bands_n=48)
+  y = torch.zeros(1, 4, 256, 2, device="cuda")
+  with pytest.raises(NotImplementedError):
+    pa.encode_compact(y)
+  pa3 = audiocodec_b200.PsychoacousticModel(44100, 256)
+  with pytest.raises(NotImplementedError):
+    pa3.encode_compact(torch.zeros(1, 4, 256, 3, device="cuda"))    # three channels: no tile kernel
+  with pytest.raises(NotImplementedError):                          # N = 64: filters wider than three bark bands
+    audiocodec_b200.PsychoacousticModel(44100, 64).encode_compact(torch.zeros(1, 4, 64, 2, device="cuda"))
+  q, bark = pa3.encode_compact(torch.zeros(0, 4, 256, 2, device="cuda"))
+  assert q.shape == (0, 4, 256, 2) and bark.shape == (0, 4, 2, 64)
+
+
 def test_unaligned_views_take_the_generic_kernel():
   """A 4-byte-aligned view (odd float offset into a larger buffer) must not reach the vectorised tile kernels."""
   n, c = 256, 2
