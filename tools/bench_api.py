@@ -45,5 +45,13 @@ timeit("quantize", lambda: pa.quantize(y, thr), 3 * E)
 timeit("dequantize", lambda: pa.dequantize(q, thr), 3 * E)
 timeit("encode (threshold + quantise)", lambda: pa.encode(y), 3 * E)
 timeit("encode, q only", lambda: pa.encode(y, return_threshold=False), 2 * E)
+G = None
+try:
+  _, G = pa.encode_compact(y)
+except NotImplementedError:
+  pass
+if G is not None:
+  timeit("encode_compact (q + bark thresholds)", lambda: pa.encode_compact(y), 2 * E + G.numel() * 4)
+  timeit("expand_threshold", lambda: pa.expand_threshold(G), E + G.numel() * 4)
 timeit("inverse_transform_dequantized", lambda: mdct.inverse_transform_dequantized(q, thr), 3 * E)
 timeit("add_noise", lambda: pa.add_noise(y, thr, seed=1), 3 * E)
