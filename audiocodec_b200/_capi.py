@@ -34,6 +34,8 @@ SIGNATURES = {
   "ac_mdct_inverse_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
   "ac_mdct_inverse_dequant_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64,
                                                  ctypes.c_int, _c_void_p]),
+  "ac_mdct_inverse_dequant_compact_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, ctypes.c_float,
+                                                         _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
   "ac_pa_plan_create": (ctypes.c_int, [ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                        ctypes.POINTER(_c_void_p)]),
   "ac_pa_plan_destroy": (ctypes.c_int, [_c_void_p]),

@@ -470,6 +470,29 @@ int ac_mdct_inverse_dequant_f32(const ac_mdct_plan* plan, const int32_t* q, cons
   return inverse_common(plan, nullptr, q, thr, x, batches, blocks, channels, stream);
 }
 
+int ac_mdct_inverse_dequant_compact_f32(const ac_mdct_plan* plan, const ac_pa_plan* pa_plan, const int32_t* q,
+                                        const float* bark_thr, float thr_scale, float* x, int64_t batches, int64_t blocks,
+                                        int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (pa_plan == nullptr) return fail(AC_ERR_INVALID, "psychoacoustic plan is null");
+  if (pa_plan->device != plan->device || pa_plan->tb.n != plan->tb.n)
+    return fail(AC_ERR_INVALID, "the two plans must share the device and filter_bands_n");
+  if (!(thr_scale > 0.f)) return fail(AC_ERR_INVALID, "thr_scale must be positive");
+  if (blocks + 1 > 2147483647LL / 2) return fail(AC_ERR_INVALID, "too many blocks per batch row");
+  if (batches == 0) return AC_OK;
+  if (x == nullptr) return fail(AC_ERR_INVALID, "x is null");
+  if (blocks > 0 && (q == nullptr || bark_thr == nullptr)) return fail(AC_ERR_INVALID, "null tensor");
+  if (!aligned16(x) || !aligned16(q) || !aligned16(bark_thr)) return fail(AC_ERR_INVALID, "all tensors must be 16-byte aligned");
+  const ac::PaDeviceTables& pt = pa_plan->tb;
+  if (pt.nb != 64 || !pt.tile_ok || pt.filt4 == nullptr || !(channels == 1 || channels == 2) ||
+      !(plan->tb.n == 256 || plan->tb.n == 512 || plan->tb.n == 1024))
+    return fail(AC_ERR_UNSUPPORTED, "the fused compact decoder is built for bark_bands_n == 64, <= 3 bands per filter, "
+                                    "filters_n 256 / 512 / 1024 and 1 or 2 channels (use ac_pa_expand_threshold_f32)");
+  cudaError_t err = ac::mdct_inverse_compact_tile(plan->tb, q, bark_thr, pt.filt4, pt.eps * (thr_scale * thr_scale), x,
+                                                  batches, blocks, channels, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "mdct_inverse_dequant_compact launch");
+}
+
 // ------------------------------------------------------------------------------------- psychoacoustics
 int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha, ac_pa_plan** out) {
   if (out == nullptr) return fail(AC_ERR_INVALID, "out is null");

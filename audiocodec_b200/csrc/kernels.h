@@ -103,7 +103,7 @@ struct PaDeviceTables {
   const float2* pow_inv_alpha = nullptr;
   float offset_log2 = 0.f;  // fp32(-log2(10) / 10) = gain_log2 / alpha: the masking offset in the log2 domain after ^(1/alpha)
   // compact side information: when set, the tensor-core tile kernel also writes the bark-domain
-  // thresholds G [rows][channels][64] (intensity, thr_scale^2 folded in) from which pa_expand_threshold rebuilds thr
+  // thresholds G [rows][64][channels] (intensity, thr_scale^2 folded in) from which pa_expand_threshold rebuilds thr
   float* bark_out = nullptr;
 };
 
@@ -176,11 +176,16 @@ cudaError_t dequantize(const int32_t* q, const float* thr, float* y, int64_t n, 
 cudaError_t codec_stats(const int32_t* q, int64_t n, unsigned long long* stats, cudaStream_t stream);
 cudaError_t add_noise(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, cudaStream_t stream);
 
-// compact side information: q and G [rows][channels][64] instead of q and thr [rows][N][channels]; only on the
+// compact side information: q and G [rows][64][channels] instead of q and thr [rows][N][channels]; only on the
 // tensor-core tile kernel (cudaErrorNotSupported otherwise).  pa_expand_threshold: thr = sqrt(G W_inv), the same
 // operations in the same order as phase D of the tile kernel (bit-identical step sizes in encoder and decoder).
 cudaError_t pa_encode_compact(const PaDeviceTables& tb, const float* y, float drown, float thr_scale, float* bark_out,
                               int32_t* q_out, int64_t rows, int channels, cudaStream_t stream);
+// mdct_tile_kernels.cu: inverse MDCT of q * sqrt(G W_inv), the expansion fused into the dequantisation (N = 256 / 512 /
+// 1024, 1 or 2 channels; cudaErrorInvalidConfiguration otherwise)
+cudaError_t mdct_inverse_compact_tile(const MdctDeviceTables& tb, const int32_t* q, const float* bark, const float4* filt4,
+                                      float eps_s2, float* x, int64_t batches, int64_t frames_n, int channels,
+                                      cudaStream_t stream);
 cudaError_t pa_expand_threshold(const PaDeviceTables& tb, const float* bark, float thr_scale, float* thr, int64_t rows,
                                 int channels, cudaStream_t stream);
 

@@ -376,6 +376,177 @@ mdct_inverse_dequant_tile_kernel(MdctDeviceTables tb, const int32_t* __restrict_
   }
 }
 
+// Dequantising inverse on the COMPACT side information: instead of one step per coefficient the
+// kernel loads the 64 bark-domain thresholds of each (frame, channel) - bark [frames][64][C], 1 / (N / 64) of the
+// bytes - and rebuilds the step of coefficient k as sqrt(G[b] w0 + G[b + 1] w1 + G[b + 2] w2) from the filter table
+// of the masking model (filt4[k] = { w0, w1, w2, b }, psychoacoustic.py:330-331), with the operations of phase D of
+// the masking kernel (psycho_mma_kernels.cu): the same bits as the step the encoder divided by.  One scratch tile,
+// one tile of integers and two small G tiles (double-buffered bulk loads).
+__device__ __forceinline__ float rsqrt_approx_ftz(float x) {
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
+template <typename Plan, int C, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+mdct_inverse_dequant_compact_tile_kernel(MdctDeviceTables tb, const int32_t* __restrict__ q,
+                                         const float* __restrict__ bark, const float4* __restrict__ filt4,
+                                         const float eps_s2, float* __restrict__ x, int frames_n, int tiles_per_row,
+                                         int64_t total_tiles) {
+  using S = TileShape<Plan, C, THREADS>;
+  constexpr int M = S::M, N = S::N, H = M, T = S::T, E = Plan::E, FP = S::FP, ROW = S::ROW;
+  constexpr int BUF = FP * ROW, GROW = 64 * C, GBUF = FP * GROW;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float* abuf = reinterpret_cast<float*>(smem_raw);                  // [FP][ROW]: scratch -> v
+  float* qbuf = abuf + BUF;                                          // [FP][ROW]: quantised integers
+  float* gbufs = qbuf + BUF;                                         // [2][FP][64][C]: bark-domain thresholds
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(gbufs + 2 * GBUF);    // [0..1] thresholds, [2] integers
+
+  const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = (tid >> 3) & 1;
+  float* arow = abuf + g * (2 / C) * ROW;
+  const int32_t* qrow = reinterpret_cast<const int32_t*>(qbuf) + g * (2 / C) * ROW;
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_init(&mbar[2], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue_load = [&](int64_t tile, float* dst, const void* src, int row_floats, uint64_t* bar) {   // thread 0 only
+    const int64_t b = tile / tiles_per_row;
+    const int fs = static_cast<int>(tile - b * tiles_per_row) * (FP - 1) - 1;
+    const int r_lo = fs < 0 ? 1 : 0;
+    const int r_hi = min(FP, frames_n - fs);
+    if (r_hi > r_lo) {
+      const uint32_t bytes = static_cast<uint32_t>(r_hi - r_lo) * row_floats * sizeof(float);
+      mbar_arrive_expect_tx(bar, bytes);
+      bulk_load(dst + r_lo * row_floats,
+                static_cast<const float*>(src) + (b * frames_n + (fs + r_lo)) * static_cast<int64_t>(row_floats), bytes, bar);
+    } else {
+      mbar_arrive(bar);
+    }
+  };
+  if (tid == 0 && blockIdx.x < total_tiles) {
+    issue_load(blockIdx.x, gbufs, bark, GROW, &mbar[0]);
+    issue_load(blockIdx.x, qbuf, q, ROW, &mbar[2]);
+  }
+
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    const int slot = it & 1;
+    float* gbuf = gbufs + slot * GBUF;
+    const float* grow = gbuf + g * (2 / C) * GROW;
+    const int64_t b = tile / tiles_per_row;
+    const int nb0 = static_cast<int>(tile - b * tiles_per_row) * (FP - 1);   // first output block
+    const int fs = nb0 - 1;
+    const int r_lo = fs < 0 ? 1 : 0;
+    const int r_hi = min(FP, frames_n - fs);
+    const bool more = tile + gridDim.x < total_tiles;
+    // the other G buffer was last read by the dequantisation of the previous tile, which ended in a barrier
+    if (tid == 0 && more) issue_load(tile + gridDim.x, gbufs + (slot ^ 1) * GBUF, bark, GROW, &mbar[slot ^ 1]);
+    mbar_wait(&mbar[slot], (it >> 1) & 1);
+    mbar_wait(&mbar[2], it & 1);
+    if (r_lo > 0 || r_hi < FP) {               // frames outside the signal are zero (mdctransformer.py:366)
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r_lo > 0) {
+        for (int i = tid * 4; i < ROW; i += THREADS * 4) *reinterpret_cast<float4*>(qbuf + i) = z;
+        for (int i = tid * 4; i < GROW; i += THREADS * 4) *reinterpret_cast<float4*>(gbuf + i) = z;
+      }
+      for (int i = max(r_hi, r_lo) * ROW + tid * 4; i < BUF; i += THREADS * 4) *reinterpret_cast<float4*>(qbuf + i) = z;
+      for (int i = max(r_hi, r_lo) * GROW + tid * 4; i < GBUF; i += THREADS * 4) *reinterpret_cast<float4*>(gbuf + i) = z;
+      __syncthreads();
+    }
+
+    // the quantiser steps of filter k for the two channels (C == 2) / the two frames (C == 1) of this thread group
+    auto step2 = [&](int k) {
+      const float4 f4 = __ldg(filt4 + k);
+      const int bb = __float_as_int(f4.w);
+      float2 g0, g1, g2;
+      if constexpr (C == 2) {
+        g0 = *reinterpret_cast<const float2*>(grow + 2 * bb);
+        g1 = *reinterpret_cast<const float2*>(grow + 2 * bb + 2);
+        g2 = *reinterpret_cast<const float2*>(grow + 2 * bb + 4);
+      } else {
+        g0 = make_float2(grow[bb], grow[GROW + bb]);
+        g1 = make_float2(grow[bb + 1], grow[GROW + bb + 1]);
+        g2 = make_float2(grow[bb + 2], grow[GROW + bb + 2]);
+      }
+      const float vx = fmaxf(eps_s2, fmaf(g2.x, f4.z, fmaf(g1.x, f4.y, g0.x * f4.x)));
+      const float vy = fmaxf(eps_s2, fmaf(g2.y, f4.z, fmaf(g1.y, f4.y, g0.y * f4.x)));
+      return make_float2(vx * rsqrt_approx_ftz(vx), vy * rsqrt_approx_ftz(vy));
+    };
+
+    // ---- rebuild the steps, dequantise, pre-twiddle                               (mdctransformer.py:141-148)
+    float2 v0[E], v1[E];
+#pragma unroll
+    for (int s = 0; s < E; ++s) {
+      const int n = Plan::in_index(t, s);
+      const int a1 = variant ? N - 1 - 2 * n : 2 * n;
+      const int a2 = (N - 1) - a1;
+      float2 l1 = step2(a1), l2 = step2(a2);
+      const float2 q1 = ld2<C, ROW>(reinterpret_cast<const float*>(qrow), a1);
+      const float2 q2 = ld2<C, ROW>(reinterpret_cast<const float*>(qrow), a2);
+      l1.x *= static_cast<float>(__float_as_int(q1.x));
+      l1.y *= static_cast<float>(__float_as_int(q1.y));
+      l2.x *= static_cast<float>(__float_as_int(q2.x));
+      l2.y *= static_cast<float>(__float_as_int(q2.y));
+      const float4 k4 = __ldg(&tb.pre_inv[variant * M + n]);
+      v0[s] = make_float2(fmaf(l2.x, k4.y, l1.x * k4.x), fmaf(l2.x, k4.w, l1.x * k4.z));
+      v1[s] = make_float2(fmaf(l2.y, k4.y, l1.y * k4.x), fmaf(l2.y, k4.w, l1.y * k4.z));
+    }
+    __syncthreads();                           // integers consumed by everybody: their buffer takes the next tile
+    if (tid == 0 && more) issue_load(tile + gridDim.x, qbuf, q, ROW, &mbar[2]);
+
+    fft2<Plan>(v0, v1, reinterpret_cast<float4*>(arow), t, g, tb.tw_pass1, tb.tw_pass2);
+    post_store<Plan, C, ROW>(v0, v1, arow, t, variant, tb.post_inv);
+    __syncthreads();
+
+    // ---- synthesis window + TDAC overlap-add (H_inv, mdctransformer.py:148,176-190), straight to global memory
+    const int nblk = min(FP - 1, frames_n + 1 - nb0);
+    float* xb = x + (b * (frames_n + 1) + nb0) * static_cast<int64_t>(ROW);
+    for (int idx = tid; idx < nblk * H; idx += THREADS) {
+      const int bl = idx / H, p = idx % H;
+      const float4 sw = __ldg(&tb.unfold[p]);
+      const float* vn = abuf + (bl + 1) * ROW + (H - 1 - p) * C;
+      const float* vp = abuf + bl * ROW + (H + p) * C;
+      float* xo = xb + static_cast<int64_t>(bl) * ROW;
+      if constexpr (C == 2) {
+        const float2 a = *reinterpret_cast<const float2*>(vn), c = *reinterpret_cast<const float2*>(vp);
+        *reinterpret_cast<float2*>(xo + 2 * p) = make_float2(fmaf(sw.x, a.x, sw.y * c.x), fmaf(sw.x, a.y, sw.y * c.y));
+        *reinterpret_cast<float2*>(xo + 2 * (N - 1 - p)) = make_float2(fmaf(sw.z, a.x, sw.w * c.x), fmaf(sw.z, a.y, sw.w * c.y));
+      } else {
+        xo[p] = fmaf(sw.x, vn[0], sw.y * vp[0]);
+        xo[N - 1 - p] = fmaf(sw.z, vn[0], sw.w * vp[0]);
+      }
+    }
+    __syncthreads();       // the scratch tile is rewritten by the transform of the next tile
+  }
+}
+
+template <typename Plan, int C, int THREADS, int MINB>
+cudaError_t launch_inverse_compact_tile(const MdctDeviceTables& tb, const int32_t* q, const float* bark,
+                                        const float4* filt4, float eps_s2, float* x, int64_t batches, int frames_n,
+                                        cudaStream_t stream) {
+  using S = TileShape<Plan, C, THREADS>;
+  static_assert(S::FP >= 2, "an inverse tile needs two frames");
+  constexpr size_t kSmem = (2 * static_cast<size_t>(S::FP) * S::ROW + 2 * static_cast<size_t>(S::FP) * 64 * C) * sizeof(float) + 32;
+  if (kSmem > 227 * 1024) return cudaErrorInvalidConfiguration;
+  const int tiles_per_row = (frames_n + 1 + S::FP - 2) / (S::FP - 1);
+  const int64_t total = batches * tiles_per_row;
+  constexpr int kFit = static_cast<int>((227 * 1024) / (kSmem + 1024));
+  constexpr int kMinB = kFit < 1 ? 1 : (kFit < MINB ? kFit : MINB);
+  const int64_t cap = static_cast<int64_t>(tile_sm_count()) * kMinB;
+  const unsigned grid = static_cast<unsigned>(std::min(total, cap));
+  auto kernel = mdct_inverse_dequant_compact_tile_kernel<Plan, C, THREADS, kMinB>;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem));
+  if (err != cudaSuccess) return err;
+  kernel<<<grid, THREADS, kSmem, stream>>>(tb, q, bark, filt4, eps_s2, x, frames_n, tiles_per_row, total);
+  count_launch();
+  return cudaGetLastError();
+}
+
 // Plain inverse (no fused dequantisation): the amplitudes are the only input, so the second tile buffer that the
 // dequantising kernel spends on the integers is free to double-buffer the bulk loads, and the overlap-add writes
 // its output blocks straight to global memory (coalesced 8-byte stores) instead of staging them.
@@ -585,6 +756,22 @@ cudaError_t mdct_inverse_tile(const MdctDeviceTables& tb, const float* y, const 
     default: return cudaErrorInvalidConfiguration;
   }
 #undef AC_INV
+}
+
+cudaError_t mdct_inverse_compact_tile(const MdctDeviceTables& tb, const int32_t* q, const float* bark, const float4* filt4,
+                                      float eps_s2, float* x, int64_t batches, int64_t frames_n, int C,
+                                      cudaStream_t stream) {
+  const int fn = static_cast<int>(frames_n);
+#define AC_INVC(PLAN, THREADS, MINB)                                                                                 \
+  return C == 2 ? launch_inverse_compact_tile<PLAN, 2, THREADS, MINB>(tb, q, bark, filt4, eps_s2, x, batches, fn, stream) \
+                : launch_inverse_compact_tile<PLAN, 1, THREADS, MINB>(tb, q, bark, filt4, eps_s2, x, batches, fn, stream)
+  switch (tb.n) {
+    case 256: AC_INVC(Plan256, 128, 3);
+    case 512: AC_INVC(Plan512, 128, 3);
+    case 1024: AC_INVC(Plan1024, 512, 1);
+    default: return cudaErrorInvalidConfiguration;
+  }
+#undef AC_INVC
 }
 
 }  // namespace ac

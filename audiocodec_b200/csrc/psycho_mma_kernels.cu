@@ -843,14 +843,13 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     }
     __syncthreads();
 
-    // compact side information: the tile's bark-domain thresholds G[band][item] -> bark_out[item][band]
+    // compact side information: the tile's bark-domain thresholds G[band][frame, channel] -> bark_out[frame][band][channel]
     if (tb.bark_out != nullptr) {
-      const int items_live = nf * C;
 #pragma unroll 1
-      for (int it = warp * (TI / kWarps); it < (warp + 1) * (TI / kWarps) && it < items_live; ++it) {
-        float* go = tb.bark_out + (f0 * C + it) * kNB;
-        go[lane] = G[lane * GS + it];
-        go[lane + 32] = G[(lane + 32) * GS + it];
+      for (int fl = warp * ROWS; fl < (warp + 1) * ROWS && fl < nf; ++fl) {
+        float* go = tb.bark_out + (f0 + fl) * (kNB * C);
+        *reinterpret_cast<VF*>(go + lane * C) = *reinterpret_cast<const VF*>(G + lane * GS + fl * C);
+        *reinterpret_cast<VF*>(go + (lane + 32) * C) = *reinterpret_cast<const VF*>(G + (lane + 32) * GS + fl * C);
       }
     }
 
@@ -1053,7 +1052,7 @@ cudaError_t launch_mma_tile(const PaDeviceTables& tb, const float* y, const floa
   return launch_mma_tile_q<C, false>(tb, y, ton_in, omd, thr_scale, thr_out, q_out, frames, stream);
 }
 
-// Decoder side of the compact side information: one warp per frame row rebuilds thr[row][k][c] from G[row][c][64].
+// Decoder side of the compact side information: one warp per frame row rebuilds thr[row][k][c] from G[row][64][c].
 // v = G[b] w0 + G[b + 1] w1 + G[b + 2] w2 in the order of phase D (its two-slot patterns are the same sums with a zero
 // weight), the same clamp and the same rsqrt: bit-identical to the thr the encoder quantised with.
 template <int C>
@@ -1061,27 +1060,22 @@ __global__ void __launch_bounds__(256) pa_expand_threshold_kernel(const float4* 
                                                                   const float* __restrict__ bark, const float eps_s2,
                                                                   float* __restrict__ thr, const int64_t rows,
                                                                   const int n) {
-  __shared__ float s_g[8][C][kNB + 4];
+  __shared__ float s_g[8][kNB * C];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + warp; row < rows; row += static_cast<int64_t>(gridDim.x) * 8) {
     __syncwarp();
+    const float* g = bark + row * (kNB * C);
 #pragma unroll
-    for (int c = 0; c < C; ++c) {
-      const float* g = bark + (row * C + c) * kNB;
-      s_g[warp][c][lane] = __ldcs(g + lane);
-      s_g[warp][c][lane + 32] = __ldcs(g + lane + 32);
-      if (lane < 4) s_g[warp][c][kNB + lane] = 0.f;
-    }
+    for (int i = 0; i < 2 * C; ++i) s_g[warp][32 * i + lane] = __ldcs(g + 32 * i + lane);
     __syncwarp();
     float* out = thr + row * static_cast<int64_t>(n) * C;
     for (int k = lane; k < n; k += 32) {
       const float4 f4 = __ldg(filt4 + k);
-      const int b = __float_as_int(f4.w);
+      const float* gb = &s_g[warp][__float_as_int(f4.w) * C];
       float t[C];
 #pragma unroll
       for (int c = 0; c < C; ++c) {
-        const float* g = &s_g[warp][c][b];
-        const float v = fmaxf(eps_s2, fmaf(g[2], f4.z, fmaf(g[1], f4.y, g[0] * f4.x)));
+        const float v = fmaxf(eps_s2, fmaf(gb[2 * C + c], f4.z, fmaf(gb[C + c], f4.y, gb[c] * f4.x)));
         t[c] = v * rsqrt_approx(v);
       }
       if constexpr (C == 2) {

@@ -126,6 +126,29 @@ class MDCTransformer:
       _capi.check(inverse(self._plan(y.device), y.data_ptr(), x.data_ptr(), b, m, c, stream_ptr(y.device)))
     return back(x)
 
+  def inverse_transform_compact(self, q, bark_thr, psychoacoustic, thr_scale=1.0):
+    """Decoder fusion on the compact side information of PsychoacousticModel.encode_compact: the quantiser steps are
+    rebuilt from the 64 bark-domain thresholds per (frame, channel) inside the dequantising inverse kernel. Bit-identical
+    to inverse_transform_dequantized(q, psychoacoustic.expand_threshold(bark_thr, thr_scale)).
+
+    :param q:        int32 [batches_n, blocks_n, filters_n, channels_n]
+    :param bark_thr: float32 [batches_n, blocks_n, 64, channels_n]
+    """
+    q, _ = adopt(q, "q", dtype=torch.int32)
+    g, back = adopt(bark_thr, "bark_thr")
+    if q.dim() != 4 or q.shape[2] != self.filters_n or g.dim() != 4 or \
+        g.shape != (q.shape[0], q.shape[1], 64, q.shape[3]):
+      raise ValueError("q must be [batches_n, blocks_n, filters_n, channels_n] and bark_thr [batches_n, blocks_n, 64, channels_n]")
+    if self.compute_dtype == "float64":
+      raise NotImplementedError("compact side information is built for float32 only")
+    b, m, n, c = q.shape
+    x = torch.empty((b, (m + 1) * n, c), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+      _capi.check(_capi.lib().ac_mdct_inverse_dequant_compact_f32(
+          self._plan(q.device), psychoacoustic._plan(q.device), q.data_ptr(), g.data_ptr(), float(thr_scale), x.data_ptr(),
+          b, m, c, stream_ptr(q.device)))
+    return back(x)
+
   def inverse_transform_dequantized(self, q, masking_threshold):
     """Decoder fusion: inverse_transform(q * masking_threshold) in one kernel (no reference symbol).
 

@@ -203,7 +203,7 @@ class PsychoacousticModel:
     """Like encode(), but the side information is the 64 bark-domain thresholds of every (frame, channel) instead of
     one step per coefficient: N / 64 times fewer floats to store next to q.
 
-    :return: (q int32 [B, M, N, C], bark_thr float32 [B, M, C, 64]); expand_threshold(bark_thr, thr_scale) is
+    :return: (q int32 [B, M, N, C], bark_thr float32 [B, M, 64, C]); expand_threshold(bark_thr, thr_scale) is
              bit-identical to the step of encode().
     """
     if self._f64:
@@ -212,7 +212,7 @@ class PsychoacousticModel:
     self._check_amplitudes(a)
     b, m, _, c = a.shape
     q = torch.empty(a.shape, dtype=torch.int32, device=a.device)
-    bark = torch.empty((b, m, c, 64), dtype=torch.float32, device=a.device)
+    bark = torch.empty((b, m, 64, c), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
       _capi.check(_capi.lib().ac_pa_encode_compact_f32(self._plan(a.device), a.data_ptr(), float(drown), float(thr_scale),
                                                        bark.data_ptr(), q.data_ptr(), b, m, c, stream_ptr(a.device)))
@@ -224,9 +224,9 @@ class PsychoacousticModel:
     if self._f64:
       raise NotImplementedError("compact side information is built for float32 only")
     g, back = adopt(bark_thr, "bark_thr")
-    if g.dim() != 4 or g.shape[3] != 64:
-      raise ValueError("bark_thr must be [batches, blocks, channels, 64]")
-    b, m, c, _ = g.shape
+    if g.dim() != 4 or g.shape[2] != 64:
+      raise ValueError("bark_thr must be [batches, blocks, 64, channels]")
+    b, m, _, c = g.shape
     thr = torch.empty((b, m, self.filter_bands_n, c), dtype=torch.float32, device=g.device)
     with torch.cuda.device(g.device):
       _capi.check(_capi.lib().ac_pa_expand_threshold_f32(self._plan(g.device), g.data_ptr(), float(thr_scale),

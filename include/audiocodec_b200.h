@@ -120,7 +120,7 @@ int ac_pa_encode_f32(const ac_pa_plan* plan, const float* y, float drown, float 
                      int64_t batches, int64_t blocks, int channels, void* stream);
 
 /* Compact side information (the decoder-side mapping is psychoacoustic.py:330-331): the encoder
- * writes q and the 64 bark-domain thresholds per (frame, channel) - bark_thr [B, M, C, 64], intensities with
+ * writes q and the 64 bark-domain thresholds per (frame, channel) - bark_thr [B, M, 64, C], intensities with
  * thr_scale^2 folded in - instead of one threshold per coefficient; ac_pa_expand_threshold_f32 rebuilds
  * step [B, M, N, C] = sqrt(bark_thr W_inv) with the operations of the encoder, bit-identical to the step q was
  * quantised with.  AC_ERR_UNSUPPORTED unless bark_bands_n == 64 with <= 3 bands per filter and 1/2/4 channels. */
@@ -129,6 +129,13 @@ int ac_pa_encode_compact_f32(const ac_pa_plan* plan, const float* y, float drown
                              int64_t batches, int64_t blocks, int channels, void* stream);
 int ac_pa_expand_threshold_f32(const ac_pa_plan* plan, const float* bark_thr, float thr_scale, float* thr,
                                int64_t batches, int64_t blocks, int channels, void* stream);
+/* Decoder fusion on the compact side information: x = inverse MDCT of q * sqrt(bark_thr W_inv), the expansion done
+ * inside the dequantising inverse kernel (it reads q and N / 64 times fewer threshold bytes).  Same result, bit for
+ * bit, as ac_pa_expand_threshold_f32 followed by ac_mdct_inverse_dequant_f32.  filters_n 256 / 512 / 1024, 1 or 2
+ * channels; AC_ERR_UNSUPPORTED otherwise. */
+int ac_mdct_inverse_dequant_compact_f32(const ac_mdct_plan* plan, const ac_pa_plan* pa_plan, const int32_t* q,
+                                        const float* bark_thr, float thr_scale, float* x,
+                                        int64_t batches, int64_t blocks, int channels, void* stream);
 
 /* PsychoacousticModel.add_noise (psychoacoustic.py:150-167): out = y + thr * N(0, 1/6), counter-based RNG. */
 int ac_pa_add_noise_f32(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, void* stream);

@@ -297,11 +297,18 @@ def test_compact_side_information_rebuilds_the_step_bit_for_bit(sr, n, c, b, m):
   pa = audiocodec_b200.PsychoacousticModel(sr, n)
   q, step = pa.encode(y, thr_scale=1.5, drown=0.25)
   qc, bark = pa.encode_compact(y, thr_scale=1.5, drown=0.25)
-  assert bark.shape == (b, m, c, 64) and torch.isfinite(bark).all() and bark.min().item() > 0
+  assert bark.shape == (b, m, 64, c) and torch.isfinite(bark).all() and bark.min().item() > 0
   assert torch.equal(q, qc)
   rebuilt = pa.expand_threshold(bark, thr_scale=1.5)
   assert torch.equal(rebuilt, step)                         # decoder and encoder use the same step, bit for bit
   assert torch.equal(pa.dequantize(qc, rebuilt), pa.dequantize(q, step))
+  if c <= 2 and n in (256, 512, 1024):                      # fused decoder: expansion inside the inverse MDCT
+    mdct = audiocodec_b200.MDCTransformer(n)
+    x_ref = mdct.inverse_transform_dequantized(q, step)
+    assert torch.equal(mdct.inverse_transform_compact(qc, bark, pa, thr_scale=1.5), x_ref)
+  elif c <= 2:
+    with pytest.raises(NotImplementedError):
+      audiocodec_b200.MDCTransformer(n).inverse_transform_compact(qc, bark, pa, thr_scale=1.5)
 
 
 def test_compact_side_information_unsupported_configurations():
@@ -315,7 +322,7 @@ def test_compact_side_information_unsupported_configurations():
   with pytest.raises(NotImplementedError):                          # N = 64: filters wider than three bark bands
     audiocodec_b200.PsychoacousticModel(44100, 64).encode_compact(torch.zeros(1, 4, 64, 2, device="cuda"))
   q, bark = pa3.encode_compact(torch.zeros(0, 4, 256, 2, device="cuda"))
-  assert q.shape == (0, 4, 256, 2) and bark.shape == (0, 4, 2, 64)
+  assert q.shape == (0, 4, 256, 2) and bark.shape == (0, 4, 64, 2)
 
 
 def test_unaligned_views_take_the_generic_kernel():
