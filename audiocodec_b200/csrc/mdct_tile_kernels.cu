@@ -381,7 +381,8 @@ mdct_inverse_dequant_tile_kernel(MdctDeviceTables tb, const int32_t* __restrict_
 // bytes - and rebuilds the step of coefficient k as sqrt(G[b] w0 + G[b + 1] w1 + G[b + 2] w2) from the filter table
 // of the masking model (filt4[k] = { w0, w1, w2, b }, psychoacoustic.py:330-331), with the operations of phase D of
 // the masking kernel (psycho_mma_kernels.cu): the same bits as the step the encoder divided by.  One scratch tile,
-// one tile of integers and two small G tiles (double-buffered bulk loads).
+// one tile of integers and one small G tile, each re-armed for the next tile as soon as every thread has consumed it
+// (72 KB at N = 256: three CTAs per SM).
 __device__ __forceinline__ float rsqrt_approx_ftz(float x) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -400,8 +401,8 @@ mdct_inverse_dequant_compact_tile_kernel(MdctDeviceTables tb, const int32_t* __r
   extern __shared__ __align__(128) unsigned char smem_raw[];
   float* abuf = reinterpret_cast<float*>(smem_raw);                  // [FP][ROW]: scratch -> v
   float* qbuf = abuf + BUF;                                          // [FP][ROW]: quantised integers
-  float* gbufs = qbuf + BUF;                                         // [2][FP][64][C]: bark-domain thresholds
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(gbufs + 2 * GBUF);    // [0..1] thresholds, [2] integers
+  float* gbuf = qbuf + BUF;                                          // [FP][64][C]: bark-domain thresholds
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(gbuf + GBUF);         // [0] thresholds, [1] integers
 
   const int tid = threadIdx.x, g = tid / T, t = tid % T, variant = (tid >> 3) & 1;
   float* arow = abuf + g * (2 / C) * ROW;
@@ -409,7 +410,6 @@ mdct_inverse_dequant_compact_tile_kernel(MdctDeviceTables tb, const int32_t* __r
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
-    mbar_init(&mbar[2], 1);
     mbar_fence_init();
   }
   __syncthreads();
@@ -429,25 +429,20 @@ mdct_inverse_dequant_compact_tile_kernel(MdctDeviceTables tb, const int32_t* __r
     }
   };
   if (tid == 0 && blockIdx.x < total_tiles) {
-    issue_load(blockIdx.x, gbufs, bark, GROW, &mbar[0]);
-    issue_load(blockIdx.x, qbuf, q, ROW, &mbar[2]);
+    issue_load(blockIdx.x, gbuf, bark, GROW, &mbar[0]);
+    issue_load(blockIdx.x, qbuf, q, ROW, &mbar[1]);
   }
 
   int it = 0;
   for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-    const int slot = it & 1;
-    float* gbuf = gbufs + slot * GBUF;
-    const float* grow = gbuf + g * (2 / C) * GROW;
     const int64_t b = tile / tiles_per_row;
     const int nb0 = static_cast<int>(tile - b * tiles_per_row) * (FP - 1);   // first output block
     const int fs = nb0 - 1;
     const int r_lo = fs < 0 ? 1 : 0;
     const int r_hi = min(FP, frames_n - fs);
     const bool more = tile + gridDim.x < total_tiles;
-    // the other G buffer was last read by the dequantisation of the previous tile, which ended in a barrier
-    if (tid == 0 && more) issue_load(tile + gridDim.x, gbufs + (slot ^ 1) * GBUF, bark, GROW, &mbar[slot ^ 1]);
-    mbar_wait(&mbar[slot], (it >> 1) & 1);
-    mbar_wait(&mbar[2], it & 1);
+    mbar_wait(&mbar[0], it & 1);
+    mbar_wait(&mbar[1], it & 1);
     if (r_lo > 0 || r_hi < FP) {               // frames outside the signal are zero (mdctransformer.py:366)
       const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r_lo > 0) {
@@ -459,33 +454,43 @@ mdct_inverse_dequant_compact_tile_kernel(MdctDeviceTables tb, const int32_t* __r
       __syncthreads();
     }
 
-    // the quantiser steps of filter k for the two channels (C == 2) / the two frames (C == 1) of this thread group
-    auto step2 = [&](int k) {
-      const float4 f4 = __ldg(filt4 + k);
-      const int bb = __float_as_int(f4.w);
-      float2 g0, g1, g2;
-      if constexpr (C == 2) {
-        g0 = *reinterpret_cast<const float2*>(grow + 2 * bb);
-        g1 = *reinterpret_cast<const float2*>(grow + 2 * bb + 2);
-        g2 = *reinterpret_cast<const float2*>(grow + 2 * bb + 4);
-      } else {
-        g0 = make_float2(grow[bb], grow[GROW + bb]);
-        g1 = make_float2(grow[bb + 1], grow[GROW + bb + 1]);
-        g2 = make_float2(grow[bb + 2], grow[GROW + bb + 2]);
+    // ---- the quantiser steps of the tile: abuf[frame][k][c] = sqrt(G W_inv), thread <-> filter k (its table entry
+    // stays in registers for all frames; neighbouring filters read the same bands of G: shared-memory broadcasts)
+    {
+      static_assert(N % THREADS == 0, "filters per thread");
+#pragma unroll
+      for (int kk = 0; kk < N / THREADS; ++kk) {
+        const int k = tid + kk * THREADS;
+        const float4 f4 = __ldg(filt4 + k);
+        const float* gk = gbuf + __float_as_int(f4.w) * C;
+#pragma unroll 4
+        for (int f = 0; f < FP; ++f) {
+          const float* gr = gk + f * GROW;
+          if constexpr (C == 2) {
+            const float2 g0 = *reinterpret_cast<const float2*>(gr), g1 = *reinterpret_cast<const float2*>(gr + 2);
+            const float2 g2 = *reinterpret_cast<const float2*>(gr + 4);
+            const float vx = fmaxf(eps_s2, fmaf(g2.x, f4.z, fmaf(g1.x, f4.y, g0.x * f4.x)));
+            const float vy = fmaxf(eps_s2, fmaf(g2.y, f4.z, fmaf(g1.y, f4.y, g0.y * f4.x)));
+            *reinterpret_cast<float2*>(abuf + f * ROW + 2 * k) =
+                make_float2(vx * rsqrt_approx_ftz(vx), vy * rsqrt_approx_ftz(vy));
+          } else {
+            const float v = fmaxf(eps_s2, fmaf(gr[2], f4.z, fmaf(gr[1], f4.y, gr[0] * f4.x)));
+            abuf[f * ROW + k] = v * rsqrt_approx_ftz(v);
+          }
+        }
       }
-      const float vx = fmaxf(eps_s2, fmaf(g2.x, f4.z, fmaf(g1.x, f4.y, g0.x * f4.x)));
-      const float vy = fmaxf(eps_s2, fmaf(g2.y, f4.z, fmaf(g1.y, f4.y, g0.y * f4.x)));
-      return make_float2(vx * rsqrt_approx_ftz(vx), vy * rsqrt_approx_ftz(vy));
-    };
+      __syncthreads();                         // thresholds consumed by everybody: their buffer takes the next tile
+      if (tid == 0 && more) issue_load(tile + gridDim.x, gbuf, bark, GROW, &mbar[0]);
+    }
 
-    // ---- rebuild the steps, dequantise, pre-twiddle                               (mdctransformer.py:141-148)
+    // ---- dequantise, pre-twiddle                               (mdctransformer.py:141-148)
     float2 v0[E], v1[E];
 #pragma unroll
     for (int s = 0; s < E; ++s) {
       const int n = Plan::in_index(t, s);
       const int a1 = variant ? N - 1 - 2 * n : 2 * n;
       const int a2 = (N - 1) - a1;
-      float2 l1 = step2(a1), l2 = step2(a2);
+      float2 l1 = ld2<C, ROW>(arow, a1), l2 = ld2<C, ROW>(arow, a2);
       const float2 q1 = ld2<C, ROW>(reinterpret_cast<const float*>(qrow), a1);
       const float2 q2 = ld2<C, ROW>(reinterpret_cast<const float*>(qrow), a2);
       l1.x *= static_cast<float>(__float_as_int(q1.x));
@@ -497,7 +502,7 @@ mdct_inverse_dequant_compact_tile_kernel(MdctDeviceTables tb, const int32_t* __r
       v1[s] = make_float2(fmaf(l2.y, k4.y, l1.y * k4.x), fmaf(l2.y, k4.w, l1.y * k4.z));
     }
     __syncthreads();                           // integers consumed by everybody: their buffer takes the next tile
-    if (tid == 0 && more) issue_load(tile + gridDim.x, qbuf, q, ROW, &mbar[2]);
+    if (tid == 0 && more) issue_load(tile + gridDim.x, qbuf, q, ROW, &mbar[1]);
 
     fft2<Plan>(v0, v1, reinterpret_cast<float4*>(arow), t, g, tb.tw_pass1, tb.tw_pass2);
     post_store<Plan, C, ROW>(v0, v1, arow, t, variant, tb.post_inv);
@@ -531,7 +536,7 @@ cudaError_t launch_inverse_compact_tile(const MdctDeviceTables& tb, const int32_
                                         cudaStream_t stream) {
   using S = TileShape<Plan, C, THREADS>;
   static_assert(S::FP >= 2, "an inverse tile needs two frames");
-  constexpr size_t kSmem = (2 * static_cast<size_t>(S::FP) * S::ROW + 2 * static_cast<size_t>(S::FP) * 64 * C) * sizeof(float) + 32;
+  constexpr size_t kSmem = (2 * static_cast<size_t>(S::FP) * S::ROW + static_cast<size_t>(S::FP) * 64 * C) * sizeof(float) + 32;
   if (kSmem > 227 * 1024) return cudaErrorInvalidConfiguration;
   const int tiles_per_row = (frames_n + 1 + S::FP - 2) / (S::FP - 1);
   const int64_t total = batches * tiles_per_row;

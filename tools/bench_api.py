@@ -53,5 +53,22 @@ except NotImplementedError:
 if G is not None:
   timeit("encode_compact (q + bark thresholds)", lambda: pa.encode_compact(y), 2 * E + G.numel() * 4)
   timeit("expand_threshold", lambda: pa.expand_threshold(G), E + G.numel() * 4)
+  try:
+    timeit("inverse_transform_compact", lambda: mdct.inverse_transform_compact(q, G, pa), 2 * E + G.numel() * 4)
+
+    def chain_compact():
+      yy = mdct.transform(x)
+      qq, gg = pa.encode_compact(yy)
+      return mdct.inverse_transform_compact(qq, gg, pa)
+
+    def chain_plain():
+      yy = mdct.transform(x)
+      qq, st = pa.encode(yy)
+      return mdct.inverse_transform_dequantized(qq, st)
+
+    timeit("chain, per-coefficient steps", chain_plain, 8 * E)
+    timeit("chain, compact side information", chain_compact, 6 * E + 2 * G.numel() * 4)
+  except NotImplementedError:
+    pass
 timeit("inverse_transform_dequantized", lambda: mdct.inverse_transform_dequantized(q, thr), 3 * E)
 timeit("add_noise", lambda: pa.add_noise(y, thr, seed=1), 3 * E)
