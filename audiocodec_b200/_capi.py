@@ -18,7 +18,7 @@ _c_void_p = ctypes.c_void_p
 _c_float_p = ctypes.POINTER(ctypes.c_float)
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 
-# name -> (restype, argtypes); mirrors the header one to one (tests/test_capi_symbols.py cross-checks it)
+# name -> (restype, argtypes); mirrors the header one to one (tests/test_host_side.py::test_library_exports_every_declared_symbol cross-checks the names)
 SIGNATURES = {
   "ac_last_error": (ctypes.c_char_p, []),
   "ac_abi_version": (ctypes.c_int, []),

@@ -2,7 +2,10 @@
 
 PyTorch is used for allocation and stream bookkeeping only; every computation goes through the C ABI.
 Foreign tensors (anything exposing __dlpack__, e.g. TensorFlow eager tensors) are viewed zero-copy and
-results are handed back in the caller's framework.
+results are handed back in the caller's framework.  The kernels need C-contiguous, 16-byte aligned tensors: a
+C-contiguous aligned input is passed as is (no copy); a strided view or a mis-aligned slice is compacted into a
+fresh device buffer first - one extra device-to-device pass, made visible by `adopt.copies` (tests assert it stays 0
+on the hot path).  The raw C ABI and the *_dl entry points never copy: they refuse such tensors with AC_ERR_INVALID.
 """
 
 import numpy as np
@@ -48,10 +51,15 @@ def adopt(x, name, dtype=torch.float32):
     raise TypeError(f"{name}: dtype {x.dtype} does not match the compute dtype {dtype} (no implicit casting)")
   if not x.is_cuda:
     raise RuntimeError(f"{name}: tensor is on {x.device}; audiocodec_b200 only runs on CUDA devices (no CPU path)")
-  x = x.contiguous()
-  if x.data_ptr() % 16 != 0:
-    x = x.clone()
+  if not x.is_contiguous() or x.data_ptr() % 16 != 0:
+    adopt.copies += 1              # the one place a tensor is copied: strided or mis-aligned input (see module docstring)
+    x = x.contiguous() if not x.is_contiguous() else x.clone()
+    if x.data_ptr() % 16 != 0:
+      x = x.clone()
   return x, back
+
+
+adopt.copies = 0
 
 
 def torch_dtype(name):

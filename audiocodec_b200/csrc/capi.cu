@@ -370,11 +370,9 @@ int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_m
       if (r2 > 1) build(r2, r0 * r1, tw_pass2);
     }
   }
-  std::vector<float> cos_table;
-  if (!fast) {
-    cos_table.resize(static_cast<size_t>(8) * n);
-    for (int m = 0; m < 8 * n; ++m) cos_table[m] = (float)std::cos(pi * m / (4.0 * n));
-  }
+  // the O(N^2) kernels' table: generic N, and power-of-two N whose any-channel tile does not fit in shared memory
+  std::vector<float> cos_table(static_cast<size_t>(8) * n);
+  for (int m = 0; m < 8 * n; ++m) cos_table[m] = (float)std::cos(pi * m / (4.0 * n));
   plan->tb.n = n;
   plan->tb.scale_fwd = (float)scale_fwd;
   plan->tb.scale_inv = (float)scale_inv;
@@ -421,9 +419,16 @@ int ac_mdct_plan_destroy(ac_mdct_plan* plan) {
   return AC_OK;
 }
 
-static int check_common(const void* plan, int64_t batches, int64_t len, int channels) {
+// plans hold device tables: a call with another device current would hand the kernels foreign pointers
+template <typename PlanT>
+static int check_common(const PlanT* plan, int64_t batches, int64_t len, int channels) {
   if (plan == nullptr) return fail(AC_ERR_INVALID, "plan is null");
   if (batches < 0 || len < 0 || channels < 1) return fail(AC_ERR_INVALID, "negative size or channels < 1");
+  int dev = -1;
+  cudaError_t err = cudaGetDevice(&dev);
+  if (err != cudaSuccess) return cuda_fail(err, "cudaGetDevice");
+  if (dev != plan->device)
+    return fail(AC_ERR_INVALID, "plan was created on cuda:%d but the current device is cuda:%d", plan->device, dev);
   return AC_OK;
 }
 
@@ -682,6 +687,7 @@ int ac_pa_tonality_f32(const ac_pa_plan* plan, const float* y, float* ton, int64
   if (int rc = check_common(plan, batches, blocks, channels)) return rc;
   if (batches * blocks == 0) return AC_OK;
   if (y == nullptr || ton == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  if (!aligned16(y)) return fail(AC_ERR_INVALID, "y must be 16-byte aligned");
   cudaError_t err = ac::pa_tonality(plan->tb, y, ton, batches * blocks, channels, static_cast<cudaStream_t>(stream));
   return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_tonality launch");
 }

@@ -386,18 +386,20 @@ cudaError_t mdct_forward(const MdctDeviceTables& tb, const float* x, float* y, i
   if (batches == 0) return cudaSuccess;
   if (!legacy_path() && mdct_tile_forward_supported(tb.n, C)) return mdct_forward_tile(tb, x, y, batches, blocks_n, C, stream);
   const int bn = static_cast<int>(blocks_n);
+  cudaError_t tiled = cudaErrorInvalidConfiguration;   // a tile that does not fit in shared memory: generic kernel below
   switch (tb.n) {
-    case 16: return launch_forward<Plan16, 128>(tb, x, y, batches, bn, C, stream);
-    case 32: return launch_forward<Plan32, 128>(tb, x, y, batches, bn, C, stream);
-    case 64: return launch_forward<Plan64, 256>(tb, x, y, batches, bn, C, stream);
-    case 128: return launch_forward<Plan128, 256>(tb, x, y, batches, bn, C, stream);
-    case 256: return launch_forward<Plan256, 256>(tb, x, y, batches, bn, C, stream);
-    case 512: return launch_forward<Plan512, 256>(tb, x, y, batches, bn, C, stream);
-    case 1024: return launch_forward<Plan1024, 256>(tb, x, y, batches, bn, C, stream);
-    case 2048: return launch_forward<Plan2048, 256>(tb, x, y, batches, bn, C, stream);
-    case 4096: return launch_forward<Plan4096, 256>(tb, x, y, batches, bn, C, stream);
+    case 16: tiled = launch_forward<Plan16, 128>(tb, x, y, batches, bn, C, stream); break;
+    case 32: tiled = launch_forward<Plan32, 128>(tb, x, y, batches, bn, C, stream); break;
+    case 64: tiled = launch_forward<Plan64, 256>(tb, x, y, batches, bn, C, stream); break;
+    case 128: tiled = launch_forward<Plan128, 256>(tb, x, y, batches, bn, C, stream); break;
+    case 256: tiled = launch_forward<Plan256, 256>(tb, x, y, batches, bn, C, stream); break;
+    case 512: tiled = launch_forward<Plan512, 256>(tb, x, y, batches, bn, C, stream); break;
+    case 1024: tiled = launch_forward<Plan1024, 256>(tb, x, y, batches, bn, C, stream); break;
+    case 2048: tiled = launch_forward<Plan2048, 256>(tb, x, y, batches, bn, C, stream); break;
+    case 4096: tiled = launch_forward<Plan4096, 256>(tb, x, y, batches, bn, C, stream); break;
     default: break;
   }
+  if (tiled != cudaErrorInvalidConfiguration) return tiled;
   const int64_t rows = batches * (blocks_n + 1);
   if (rows > 2147483647LL || C > 65535) return cudaErrorInvalidConfiguration;
   dim3 grid(static_cast<unsigned>(rows), static_cast<unsigned>(C));
@@ -412,25 +414,34 @@ cudaError_t mdct_inverse(const MdctDeviceTables& tb, const float* y, const int32
   if (!legacy_path() && mdct_tile_inverse_supported(tb.n, C))
     return mdct_inverse_tile(tb, y, q, thr, x, batches, frames_n, C, stream);
   const int fn = static_cast<int>(frames_n);
+  cudaError_t tiled = cudaErrorInvalidConfiguration;
   switch (tb.n) {
-    case 16: return launch_inverse<Plan16, 128>(tb, y, q, thr, x, batches, fn, C, stream);
-    case 32: return launch_inverse<Plan32, 128>(tb, y, q, thr, x, batches, fn, C, stream);
-    case 64: return launch_inverse<Plan64, 256>(tb, y, q, thr, x, batches, fn, C, stream);
-    case 128: return launch_inverse<Plan128, 256>(tb, y, q, thr, x, batches, fn, C, stream);
-    case 256: return launch_inverse<Plan256, 256>(tb, y, q, thr, x, batches, fn, C, stream);
-    case 512: return launch_inverse<Plan512, 256>(tb, y, q, thr, x, batches, fn, C, stream);
-    case 1024: return launch_inverse<Plan1024, 256>(tb, y, q, thr, x, batches, fn, C, stream);
-    case 2048: return launch_inverse<Plan2048, 256>(tb, y, q, thr, x, batches, fn, C, stream);
-    case 4096: return launch_inverse<Plan4096, 256>(tb, y, q, thr, x, batches, fn, C, stream);
+    case 16: tiled = launch_inverse<Plan16, 128>(tb, y, q, thr, x, batches, fn, C, stream); break;
+    case 32: tiled = launch_inverse<Plan32, 128>(tb, y, q, thr, x, batches, fn, C, stream); break;
+    case 64: tiled = launch_inverse<Plan64, 256>(tb, y, q, thr, x, batches, fn, C, stream); break;
+    case 128: tiled = launch_inverse<Plan128, 256>(tb, y, q, thr, x, batches, fn, C, stream); break;
+    case 256: tiled = launch_inverse<Plan256, 256>(tb, y, q, thr, x, batches, fn, C, stream); break;
+    case 512: tiled = launch_inverse<Plan512, 256>(tb, y, q, thr, x, batches, fn, C, stream); break;
+    case 1024: tiled = launch_inverse<Plan1024, 256>(tb, y, q, thr, x, batches, fn, C, stream); break;
+    case 2048: tiled = launch_inverse<Plan2048, 256>(tb, y, q, thr, x, batches, fn, C, stream); break;
+    case 4096: tiled = launch_inverse<Plan4096, 256>(tb, y, q, thr, x, batches, fn, C, stream); break;
     default: break;
   }
+  if (tiled != cudaErrorInvalidConfiguration) return tiled;
   const int64_t rows = batches * (frames_n + 1);
   if (rows > 2147483647LL || C > 65535) return cudaErrorInvalidConfiguration;
   dim3 grid(static_cast<unsigned>(rows), static_cast<unsigned>(C));
-  const size_t smem = 3 * static_cast<size_t>(tb.n) * sizeof(float);
+  const size_t smem = 3 * static_cast<size_t>(tb.n) * sizeof(float);   // above 48 KB for filters_n > 4096: opt in
+  cudaError_t err;
   if (q != nullptr) {
+    err = cudaFuncSetAttribute(mdct_inverse_generic_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
     mdct_inverse_generic_kernel<true><<<grid, 128, smem, stream>>>(tb, y, q, thr, x, fn, C);
   } else {
+    err = cudaFuncSetAttribute(mdct_inverse_generic_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               static_cast<int>(smem));
+    if (err != cudaSuccess) return err;
     mdct_inverse_generic_kernel<false><<<grid, 128, smem, stream>>>(tb, y, q, thr, x, fn, C);
   }
   count_launch();

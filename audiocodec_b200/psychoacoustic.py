@@ -249,8 +249,23 @@ class PsychoacousticModel:
 
     :return: (q, step, thr_scale); bit_estimate(q)["bits"] <= bits_per_coefficient * q.numel()
     """
+    if self.compute_dtype != "float32":
+      raise NotImplementedError("encode_at_bitrate: the rate loop is built on the float32 fused encoder only")
     target = float(bits_per_coefficient) * mdct_amplitudes.numel()
     lo, hi = -10.0, 10.0                      # log2(scale): bits fall monotonically as the scale grows
+
+    def bits_at(log2_scale):
+      return self.bit_estimate(self.encode(mdct_amplitudes, drown=drown, thr_scale=2.0 ** log2_scale,
+                                           return_threshold=False))["bits"]
+
+    # both ends of the bracket first: widen it (up to 2^+-40) when the target lies outside, refuse what no scale reaches
+    while bits_at(hi) > target:
+      if hi >= 40.0:
+        raise ValueError(f"encode_at_bitrate: {bits_per_coefficient} bits per coefficient is not reachable "
+                         f"(even thr_scale = 2^{hi:.0f} needs more)")
+      lo, hi = hi, hi + 10.0
+    while lo > -40.0 and bits_at(lo) <= target:
+      lo, hi = lo - 10.0, lo                  # the finest bracket end already fits: move towards finer steps
     for _ in range(int(iterations)):
       mid = 0.5 * (lo + hi)
       q = self.encode(mdct_amplitudes, drown=drown, thr_scale=2.0 ** mid, return_threshold=False)

@@ -60,6 +60,15 @@ def describe(name):
           "mdct_forward -> pa_encode(tonality+threshold+quantise) -> mdct_inverse_dequant")
 
 
+def bench_config(name, b, c, s, n):
+  """The `config` object of the JSON line: the same for the GPU arm and the reference arm (the driver compares them)."""
+  mb = 4e-6 * b * c * (s // n + 1) * n
+  return {"workload": describe(name) if b == WORKLOADS[name][0] else describe(name) + f" (batch {b})",
+          "per_gpu_clips": b,
+          "l2": "inputs larger than L2 (x, Y, q, step, x_hat are %.0f MB each; L2 is 126 MB)" % mb,
+          "timing": "GPU arm: CUDA events on the launching stream, max over ranks; reference arm: host wall clock"}
+
+
 # ------------------------------------------------------------------------------------------ CPU port
 def _oracle_chain(x, mdct, pa, oracle):
   y = mdct.transform(x)
@@ -127,8 +136,9 @@ def run_reference_arm(args):
     "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
     "warmup": args.warmup, "ms_per_step": 1e3 * info["seconds"] / args.steps, "higher_is_better": True,
     "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-    "config": {"workload": describe(args.workload), "note": "CPU port of the reference path (NumPy oracle); the "
-               "reference itself needs TensorFlow, which is not installable offline"},
+    "config": bench_config(args.workload, b, c, s, n),
+    "note": "CPU port of the reference path (NumPy oracle); the reference itself needs TensorFlow, which is not "
+            "installable offline",
     "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]},
     "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     "gpu_launches": 0,
@@ -360,9 +370,7 @@ def run_b200_arm(args):
       "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
       "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
       "dtype": "f32", "data": "synthetic",
-      "config": {"workload": describe(args.workload) if not args.batch else describe(args.workload) + f" (batch {b})",
-                 "per_gpu_clips": b, "l2": "inputs larger than L2 (x, Y, q, step, x_hat are %.0f MB each; L2 is 126 MB)"
-                 % (4e-6 * rows * frames * n), "timing": "CUDA events on the launching stream, max over ranks"},
+      "config": bench_config(args.workload, b, c, s, n),
       "e2e": {"value": audio_s_per_step / (e2e_ms * 1e-3) if e2e_steps else None, "unit": UNIT,
               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms if e2e_steps else None,
               "steps": e2e_steps,
@@ -371,6 +379,8 @@ def run_b200_arm(args):
       "roofline": {"bound": "hbm", "kernel": dominant, "achieved": per_kernel[dominant]["gbs"], "peak": peak,
                    "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
                    "unit": "GB/s", "frac": per_kernel[dominant]["frac"], "traffic": traffic,
+                   "traffic_source": "profiles/dram_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                     "ncu --set full capture of this kernel on this workload; not measured in this run)",
                    "chain_gbs": sum(alg_bytes.values()) / (ms_per_step * 1e-3) / 1e9,
                    "chain_frac": sum(alg_bytes.values()) / (ms_per_step * 1e-3) / 1e9 / peak},
       "kernels": per_kernel,
@@ -379,7 +389,7 @@ def run_b200_arm(args):
                 "roundtrip_rms_error": err, "finite": ok},
     }
     if world == 1 and not args.no_cpu_baseline:
-      v, info = cpu_port_throughput(args.workload, budget_s=15.0, steps=1, warmup=0)
+      v, info = cpu_port_throughput(args.workload, budget_s=20.0, steps=2, warmup=1)
       line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
     print(json.dumps(line))
   if world > 1:

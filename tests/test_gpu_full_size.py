@@ -1,0 +1,156 @@
+"""Whole-tensor parity of the CUDA path against the oracle on the BASELINE.json configurations.
+
+Every clip of the GPU result is compared with the oracle run on the same clip (thread pool over clips, the way
+bench.py's cpu_baseline leg runs it): cfg1 and cfg2 complete, cfg3 / cfg4 / the per-GPU shard of cfg5 on the first
+clips of a full-length batch.  Per clip:
+
+  * Y, tonality, thr against the float64 oracle          -> <= 1e-5 x signal RMS (north star), tonality <= 2e-5
+  * q against the fp32-faithful oracle (the reference's default graph computes in fp32)
+                                                          -> >= 99.99 % identical, the rest +-1
+  * q against oracle.quantize(Y_gpu, step_gpu)           -> bit-exact (quantiser fed the same threshold)
+  * x_hat against the float64 oracle IMDCT of the same dequantised coefficients
+                                                          -> <= 1e-5 x signal RMS
+  * reconstruction error rms(x_hat - x) against the fp32-faithful oracle chain's -> equal to 1e-3 relative
+
+The masking threshold, spreading matrix and quiet threshold of the oracle are pinned only through the reference
+sources run under oracle/tf_shim (the reference's own tests do not pin them, TensorFlow is absent): "green" here
+means green against that restatement.
+"""
+
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+import pytest
+import torch
+
+import audiocodec_b200
+from oracle import audiocodec_oracle as oracle
+from conftest import rms
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+class _Acc:
+  def __init__(self):
+    self.e_y = self.e_thr = self.e_ton = self.e_xhat = 0.0
+    self.q_total = self.q_diff = 0
+    self.q_maxdiff = 0
+    self.q_selfdiff = 0
+    self.err2 = self.err2_ref = 0.0
+    self.n_err = 0
+
+
+def _check_clips(sr, n, c, seconds, clips, first_clip=0, chunk=16, thr_scale=1.0):
+  """Runs `clips` clips of the workload through the CUDA chain and the oracle, clip by clip; returns the accumulator."""
+  s = (sr * seconds // n) * n
+  codec = audiocodec_b200.AudioCodec(sr, filters_n=n)
+  mdct64 = oracle.MDCTransformer(n, compute_dtype=np.float64)
+  pa64 = oracle.PsychoacousticModel(sr, n, compute_dtype=np.float64)
+  mdct32 = oracle.MDCTransformer(n, compute_dtype=np.float32)
+  pa32 = oracle.PsychoacousticModel(sr, n, compute_dtype=np.float32)
+  acc = _Acc()
+  threads = min(os.cpu_count() or 1, 16)
+  try:
+    from threadpoolctl import threadpool_limits
+    limit = threadpool_limits(limits=1)
+  except ImportError:
+    limit = None
+
+  def one_clip(args):
+    x, y, ton, thr, q, step, xhat = args           # NumPy views of one clip, batch axis kept (size 1)
+    x64 = x.astype(np.float64)
+    sig = rms(x64)
+    y_ref = mdct64.transform(x64)
+    ton_ref = pa64.tonality(y_ref)
+    thr_ref = pa64.global_masking_threshold(y_ref, ton_ref)
+    r = {"e_y": np.max(np.abs(y - y_ref)) / sig, "e_ton": np.max(np.abs(ton - ton_ref)),
+         "e_thr": max(np.max(np.abs(thr - thr_ref)), np.max(np.abs(step - thr_scale * thr_ref))) / sig}
+    # fp32-faithful reference chain for the integers and the reconstruction error
+    y32 = mdct32.transform(x)
+    thr32 = pa32.global_masking_threshold(y32, pa32.tonality(y32)) * np.float32(thr_scale)
+    q32 = oracle.quantize(y32, thr32)
+    d = np.abs(q.astype(np.int64) - q32)
+    r["q_total"], r["q_diff"], r["q_maxdiff"] = d.size, int(np.count_nonzero(d)), int(d.max())
+    r["q_selfdiff"] = int(np.count_nonzero(q != oracle.quantize(y, step)))
+    deq = oracle.dequantize(q, step).astype(np.float64)
+    r["e_xhat"] = np.max(np.abs(xhat - mdct64.inverse_transform(deq))) / sig
+    xhat32 = mdct32.inverse_transform(oracle.dequantize(q32, thr32))
+    r["err2"] = float(np.sum((xhat[:, n:-n].astype(np.float64) - x64) ** 2))
+    r["err2_ref"] = float(np.sum((xhat32[:, n:-n].astype(np.float64) - x64) ** 2))
+    r["n_err"] = x64.size
+    return r
+
+  try:
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+      for i0 in range(0, clips, chunk):
+        i1 = min(clips, i0 + chunk)
+        x = oracle.synthetic_audio(i1 - i0, s, c, sr, first_clip=first_clip + i0)
+        xd = torch.from_numpy(x).cuda()
+        y = codec.mdct.transform(xd)
+        ton = codec.psychoacoustic.tonality(y)
+        thr = codec.psychoacoustic.global_masking_threshold(y, ton)
+        q, step = codec.encode(xd, thr_scale=thr_scale)
+        xhat = codec.decode(q, step)
+        host = [t.cpu().numpy() for t in (y, ton, thr, q, step, xhat)]
+        del xd, y, ton, thr, q, step, xhat
+        jobs = [tuple(a[j:j + 1] for a in [x] + host) for j in range(i1 - i0)]
+        for r in pool.map(one_clip, jobs):
+          acc.e_y = max(acc.e_y, r["e_y"])
+          acc.e_ton = max(acc.e_ton, r["e_ton"])
+          acc.e_thr = max(acc.e_thr, r["e_thr"])
+          acc.e_xhat = max(acc.e_xhat, r["e_xhat"])
+          acc.q_total += r["q_total"]
+          acc.q_diff += r["q_diff"]
+          acc.q_maxdiff = max(acc.q_maxdiff, r["q_maxdiff"])
+          acc.q_selfdiff += r["q_selfdiff"]
+          acc.err2 += r["err2"]
+          acc.err2_ref += r["err2_ref"]
+          acc.n_err += r["n_err"]
+  finally:
+    if limit is not None:
+      limit.restore_original_limits()
+  return acc
+
+
+def _assert_parity(acc, expect_coefficients=None):
+  if expect_coefficients is not None:
+    assert acc.q_total == expect_coefficients
+  assert acc.e_y <= TOL, acc.e_y                       # MDCT coefficients, relative to the clip's RMS
+  assert acc.e_ton <= 2e-5, acc.e_ton
+  assert acc.e_thr <= TOL, acc.e_thr                   # masking threshold (stand-alone call and the fused step)
+  assert acc.e_xhat <= TOL, acc.e_xhat                 # IMDCT, relative to the clip's RMS
+  assert acc.q_selfdiff == 0                           # quantiser bit-exact given the same threshold
+  assert acc.q_maxdiff <= 1
+  assert acc.q_diff <= 1e-4 * acc.q_total, (acc.q_diff, acc.q_total)
+  err, err_ref = np.sqrt(acc.err2 / acc.n_err), np.sqrt(acc.err2_ref / acc.n_err)
+  assert abs(err - err_ref) <= 1e-3 * err_ref, (err, err_ref)
+
+
+def test_cfg1_complete():
+  """BASELINE configs[0]: mono 44.1 kHz 1 s (172 blocks of 256), batch 1 - every tensor of the round trip."""
+  acc = _check_clips(44100, 256, 1, 1, clips=1)
+  _assert_parity(acc, expect_coefficients=173 * 256)
+
+
+def test_cfg2_complete():
+  """BASELINE configs[1], the bench workload: all 64 stereo clips x 10 s, N = 256 (112.9 M coefficients)."""
+  acc = _check_clips(44100, 256, 2, 10, clips=64)
+  _assert_parity(acc, expect_coefficients=64 * 1723 * 256 * 2)
+
+
+def test_cfg3_slice():
+  """BASELINE configs[2]: N = 1024, 48 kHz stereo 30 s - 8 full-length clips."""
+  _assert_parity(_check_clips(48000, 1024, 2, 30, clips=8, chunk=8))
+
+
+def test_cfg4_slice():
+  """BASELINE configs[3]: 10 s mono, N = 256 - 32 full-length clips at a fixed threshold scale ("fixed bitrate")."""
+  _assert_parity(_check_clips(44100, 256, 1, 10, clips=32, chunk=32, thr_scale=1.5))
+
+
+def test_cfg5_shard_slice():
+  """BASELINE configs[4]: 30 s stereo 44.1 kHz, N = 256 - 32 full-length clips from the middle of rank 3's shard."""
+  _assert_parity(_check_clips(44100, 256, 2, 30, clips=32, first_clip=3 * 1024 + 500, chunk=16))

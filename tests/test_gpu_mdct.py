@@ -67,7 +67,7 @@ def test_against_reference_fixture(golden, name, n, window):
   back = mdct.inverse_transform(cuda(golden[f"mdct_{name}_f32_y"])).cpu().numpy()
   back_ref = golden[f"mdct_{name}_f64_xhat"]
   assert back.shape == back_ref.shape
-  assert np.max(np.abs(back - back_ref)) <= 2 * TOL * rms(x)
+  assert np.max(np.abs(back - back_ref)) <= TOL * rms(x)
 
 
 # ---- oracle on seeded inputs: every fast-path size, generic sizes, ragged shapes ---------------------------
@@ -99,12 +99,12 @@ def test_against_oracle(n, window, b, blocks, c):
   back = mdct.inverse_transform(y)
   assert tuple(back.shape) == (b, (blocks + 2) * n, c)
   back_ref = ref.inverse_transform(y_ref)
-  assert np.max(np.abs(back.cpu().numpy() - back_ref), initial=0.0) <= 2 * TOL * scale
+  assert np.max(np.abs(back.cpu().numpy() - back_ref), initial=0.0) <= TOL * scale
   # inverse on its own input (not a round trip): arbitrary coefficients
   coefs = rng.standard_normal((b, blocks + 3, n, c)).astype(np.float32)
   inv = mdct.inverse_transform(cuda(coefs)).cpu().numpy()
   inv_ref = ref.inverse_transform(coefs.astype(np.float64))
-  assert np.max(np.abs(inv - inv_ref)) <= 2 * TOL * max(rms(inv_ref), 1e-3)
+  assert np.max(np.abs(inv - inv_ref)) <= TOL * max(rms(inv_ref), 1e-3)
 
 
 def test_empty_batch():
@@ -263,3 +263,52 @@ def test_kernels_really_launched():
   before = _capi.lib().ac_kernel_launch_count()
   audiocodec_b200.MDCTransformer(256).transform(torch.zeros(1, 512, 1, device="cuda"))
   assert _capi.lib().ac_kernel_launch_count() == before + 1
+
+
+# ---- repeated-run determinism on ragged tiles (stand-in for racecheck: compute-sanitizer is closed on the pool) -----
+@pytest.mark.parametrize("n,b,blocks,c", [(256, 3, 37, 2), (256, 2, 129, 1), (1024, 2, 19, 2), (512, 2, 23, 1),
+                                          (256, 5, 1, 2), (64, 3, 50, 2)])
+def test_repeated_runs_are_bit_identical(n, b, blocks, c):
+  """The in-place shared-memory rows of the tile kernels (input block -> FFT scratch -> output frame, overlap-add of
+  adjacent frames) are reused without atomics: a missing barrier would show up as run-to-run differences.  Twenty runs
+  of K1, the plain K2 and the dequantising K2 on ragged tile shapes, interleaved with a kernel that perturbs timing."""
+  rng = np.random.default_rng(n + blocks)
+  x = cuda(rng.uniform(-1, 1, (b, blocks * n, c)).astype(np.float32))
+  mdct = audiocodec_b200.MDCTransformer(n)
+  y0 = mdct.transform(x)
+  back0 = mdct.inverse_transform(y0)
+  q = torch.randint(-7, 8, tuple(y0.shape), device="cuda", dtype=torch.int32)
+  step = torch.rand(tuple(y0.shape), device="cuda") + 0.01
+  deq0 = mdct.inverse_transform_dequantized(q, step)
+  junk = torch.empty(1 << 22, device="cuda")
+  for i in range(20):
+    if i % 3 == 0:
+      junk.normal_()                                            # different co-residency / cache state per run
+    assert torch.equal(mdct.transform(x), y0)
+    assert torch.equal(mdct.inverse_transform(y0), back0)
+    assert torch.equal(mdct.inverse_transform_dequantized(q, step), deq0)
+
+
+# ---- sizes behind the tuned paths (ADVICE round 1) ------------------------------------------------------------------
+@pytest.mark.parametrize("n,window,b,blocks,c", [(4100, 'sine', 1, 3, 1), (5000, 'vorbis', 1, 2, 2),
+                                                 (4096, 'vorbis', 1, 2, 6), (2048, 'vorbis', 1, 3, 12)])
+def test_generic_kernels_large_n_and_wide_tiles(n, window, b, blocks, c):
+  """Generic O(N^2) kernels with more than 48 KB of dynamic shared memory (filters_n > 4096) and power-of-two filters_n
+  whose any-channel tile does not fit in shared memory (falls through to the generic kernels).  The reference here is
+  the library's float64 path (itself pinned to the oracle at 1e-13 in test_gpu_float64.py): the oracle's dense
+  [2, N, N] tables take a minute to build at these sizes."""
+  rng = np.random.default_rng(n + c)
+  x = rng.uniform(-1, 1, (b, blocks * n, c)).astype(np.float32)
+  ref = audiocodec_b200.MDCTransformer(n, window_type=window, compute_dtype='float64')
+  mdct = audiocodec_b200.MDCTransformer(n, window_type=window)
+  y = mdct.transform(cuda(x))
+  y_ref = ref.transform(cuda(x.astype(np.float64)))
+  assert (y.double() - y_ref).abs().max().item() <= 2 * TOL * rms(x)        # O(N^2) fp32 sums: twice the FFT tolerance
+  back = mdct.inverse_transform(y)
+  assert (back.double() - ref.inverse_transform(y_ref)).abs().max().item() <= 2 * TOL * rms(x)
+  assert (back[:, n:-n] - cuda(x)).abs().max().item() <= 1e-4
+  q = torch.randint(-3, 4, tuple(y.shape), device="cuda", dtype=torch.int32)
+  step = torch.full(tuple(y.shape), 0.01, device="cuda")
+  deq = mdct.inverse_transform_dequantized(q, step)
+  deq_ref = ref.inverse_transform(q.double() * 0.01)
+  assert (deq.double() - deq_ref).abs().max().item() <= 2 * TOL * max(rms(deq_ref.cpu().numpy()), 1e-3)
