@@ -420,17 +420,18 @@ int ac_mdct_plan_destroy(ac_mdct_plan* plan) {
 }
 
 // plans hold device tables: a call with another device current would hand the kernels foreign pointers
-template <typename PlanT>
-static int check_common(const PlanT* plan, int64_t batches, int64_t len, int channels) {
-  if (plan == nullptr) return fail(AC_ERR_INVALID, "plan is null");
+static int check_sizes_and_device(bool have_plan, int plan_device, int64_t batches, int64_t len, int channels) {
+  if (!have_plan) return fail(AC_ERR_INVALID, "plan is null");
   if (batches < 0 || len < 0 || channels < 1) return fail(AC_ERR_INVALID, "negative size or channels < 1");
   int dev = -1;
   cudaError_t err = cudaGetDevice(&dev);
   if (err != cudaSuccess) return cuda_fail(err, "cudaGetDevice");
-  if (dev != plan->device)
-    return fail(AC_ERR_INVALID, "plan was created on cuda:%d but the current device is cuda:%d", plan->device, dev);
+  if (dev != plan_device)
+    return fail(AC_ERR_INVALID, "plan was created on cuda:%d but the current device is cuda:%d", plan_device, dev);
   return AC_OK;
 }
+#define check_common(plan, batches, len, channels) \
+  check_sizes_and_device((plan) != nullptr, (plan) != nullptr ? (plan)->device : 0, batches, len, channels)
 
 int ac_mdct_forward_f32(const ac_mdct_plan* plan, const float* x, float* y, int64_t batches, int64_t samples,
                         int channels, void* stream) {
