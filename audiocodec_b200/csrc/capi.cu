@@ -135,9 +135,26 @@ int unwrap_dl(struct DLManagedTensor* m, const char* name, int ndim, uint8_t cod
 // to the eight warps in contiguous runs of equal cost, and the filters of the chunk's tonality pass in contiguous runs
 // that level the warps' totals.  Host-only (no CUDA): ac_pa_mma_jobs_host exposes it to the CPU tests.  Returns
 // false when the list does not fit the kernel parameter (the kernel is then not used).
+static bool build_mma_jobs_chunk(const ac::PaTables& t, ac::PaJobParams& jp, std::vector<float>& mma_w4, int* chunk_k,
+                                 int* n_chunks_out, int* n_jobs_out, int mma_chunk_k);
+
+// filters per chunk of the masking kernel's double-buffered tile: 64 (three CTAs per SM).  32-filter chunks leave room
+// for four CTAs per SM but measured slower on B200 (0.189 against 0.171 ms on cfg2, profiles/README.md);
+// AC_PA_CHUNK=32|64 forces one (experiments; read when a plan is created).
 static bool build_mma_jobs(const ac::PaTables& t, ac::PaJobParams& jp, std::vector<float>& mma_w4, int* chunk_k,
                            int* n_chunks_out, int* n_jobs_out) {
-  const int mma_chunk_k = 64;
+  int forced = 0;
+  if (const char* e = std::getenv("AC_PA_CHUNK")) forced = std::atoi(e);
+  for (int ck : {64, 32}) {
+    if ((forced == 32 || forced == 64) && ck != forced) continue;
+    mma_w4.clear();
+    if (build_mma_jobs_chunk(t, jp, mma_w4, chunk_k, n_chunks_out, n_jobs_out, ck)) return true;
+  }
+  return false;
+}
+
+static bool build_mma_jobs_chunk(const ac::PaTables& t, ac::PaJobParams& jp, std::vector<float>& mma_w4, int* chunk_k,
+                                 int* n_chunks_out, int* n_jobs_out, const int mma_chunk_k) {
   const int mma_n_chunks = (t.n + mma_chunk_k - 1) / mma_chunk_k;
   std::vector<int4> job_desc;
   std::vector<int32_t> job_start(static_cast<size_t>(mma_n_chunks) * 9 + 1, 0);
@@ -595,6 +612,10 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
   };
   const std::vector<float2> pow_alpha = pow_table(d.alpha), pow_inv_alpha = pow_table(d.inv_alpha);
   d.offset_log2 = static_cast<float>(-std::log2(10.0) / 10.0);
+  d.pow_c1 = static_cast<float>(alpha - 0.5);
+  d.pow_c2 = static_cast<float>(1. / alpha - 2.);
+  // |c| lg2(x) keeps ~2^-24 / |c| of headroom against fp32 rounding of lg2: split powers for alpha in [0.45, 0.65]
+  d.pow_split = (alpha >= 0.45 && alpha <= 0.65 && std::getenv("AC_PA_POW_TABLE") == nullptr) ? 1 : 0;
   {
     // max(eps, masking)^(1/alpha) <= eps when alpha <= 1; the result is then raised to the quiet threshold anyway
     float quiet_min = INFINITY;
@@ -637,6 +658,17 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
     free_all(plan->owned);
     delete plan;
     return cuda_fail(err, "uploading psychoacoustic tables");
+  }
+  {
+    // ticket counters of the masking kernel's tile scheduler (zero between launches)
+    const std::vector<unsigned> zeros(static_cast<size_t>(2) * ac::kPaSchedSlots, 0u);
+    const unsigned* sched = nullptr;
+    if ((err = upload(zeros, &sched, plan->owned)) != cudaSuccess) {
+      free_all(plan->owned);
+      delete plan;
+      return cuda_fail(err, "allocating the tile scheduler counters");
+    }
+    d.sched = const_cast<unsigned*>(sched);
   }
   // float64 compute dtype (f64_kernels.cu): unrounded weights; the index arrays are shared with the fp32 plan
   {

@@ -105,7 +105,16 @@ struct PaDeviceTables {
   // compact side information: when set, the tensor-core tile kernel also writes the bark-domain
   // thresholds G [rows][64][channels] (intensity, thr_scale^2 folded in) from which pa_expand_threshold rebuilds thr
   float* bark_out = nullptr;
+  // split powers of the tensor-core tile kernel, for alpha near 1/2 (the default 0.6): x^alpha = sqrt(x) x^(alpha - 1/2)
+  // and x^(1/alpha) = x^2 x^(1/alpha - 2) - the exponent that multiplies lg2(x) is small (pow_c1 = alpha - 1/2,
+  // pow_c2 = 1/alpha - 2), so the rounding of lg2(x) (|lg2 x| up to 47) no longer limits the result and the exponent
+  // tables are not needed; pow_split == 0 keeps the table powers (any alpha)
+  int pow_split = 0;
+  float pow_c1 = 0.f, pow_c2 = 0.f;
+  // tile scheduler of the tensor-core tile kernel: kPaSchedSlots pairs of {next ticket, finished CTAs}, zero between launches
+  unsigned* sched = nullptr;
 };
+constexpr int kPaSchedSlots = 64;
 
 // psycho_mma_kernels.cu: nb == 64, <= 3 bands per filter, 1 / 2 / 4 channels
 bool pa_mma_tile_supported(const PaDeviceTables& tb, int channels);

@@ -32,6 +32,7 @@
 #include "kernels.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdint>
 #include <cstdlib>
 
@@ -62,6 +63,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __device__ __forceinline__ float lg2_approx(float x) {
   float r;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -153,12 +159,14 @@ __host__ __device__ inline Layout2 layout2(const PaDeviceTables& tb) {
   Layout2 L;
   const int kc = tb.n < tb.mma_chunk_k ? tb.n : tb.mma_chunk_k;
   const int t_rows = (kc + 3) * kTS;                    // 3 zero rows behind the chunk for the 4-filter steps
-  const int g_words = kNB * kGS;                        // G aliases the buffer of the tile's last chunk
   int o = 0;
   L.powa = o;    o += 512;                              // the exponent tables come first: an index with the sign bit
   L.powia = o;   o += 512;                              //   set (NaN input) still reads inside the allocation
-  L.tbuf = ((t_rows > g_words ? t_rows : g_words) + 3) & ~3;
+  L.tbuf = (t_rows + 3) & ~3;
   L.t = o;       o += 2 * L.tbuf;                       // two chunk buffers: one is filled while the other is read
+  // G [64][kGS] aliases P and the tonality partials behind it: both are dead once the MMA loop and the per-item
+  // constants are done, and are next written behind the first barrier of the next tile
+  static_assert(kNB * kPS + 2 * kWarps * kTI >= kNB * kGS, "G must fit into P + the tonality partials");
   L.p = o;       o += kNB * kPS;
   L.part = o;    o += 2 * kWarps * kTI;
   L.uv = o;      o += 3 * kTI;
@@ -471,12 +479,28 @@ __device__ __forceinline__ void phase_d_unit_pairs(const float4* __restrict__ fi
   }
 }
 
-template <int C, bool QUANT, int NFIX>
-__global__ void __launch_bounds__(kThreads, 3)
+#ifdef AC_PA_TRACE
+// development build only (tools/k3_trace.py): per CTA and tile, the global timer at the start of the chunk loop, of the
+// MMA phase, of phase D and at the end of phase D; slot 0 of a CTA holds its SM id
+__device__ unsigned long long* g_pa_trace = nullptr;
+__device__ __forceinline__ void pa_trace(int slot, int ev) {
+  if (threadIdx.x == 0 && g_pa_trace != nullptr && slot < 15) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_pa_trace[(static_cast<size_t>(blockIdx.x) * 16 + 1 + slot) * 4 + ev] = t;
+  }
+}
+#define PA_TRACE(slot, ev) pa_trace(slot, ev)
+#else
+#define PA_TRACE(slot, ev)
+#endif
+
+template <int C, bool QUANT, int NFIX, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB)
 pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_constant__ PaJobParams jp,
                    const float* __restrict__ y, const float* __restrict__ ton_in, float one_minus_drown, float thr_scale,
                    float* __restrict__ thr_out, int32_t* __restrict__ q_out, int64_t frames_total, int64_t tiles,
-                   const int ablate) {
+                   unsigned* __restrict__ sched, const int ablate) {
   using VF = typename Vec<C>::F;
   using VI = typename Vec<C>::I;
   constexpr int TI = kTI, TS = kTS, GS = kGS, PS = kPS;
@@ -557,6 +581,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   const uint32_t w_base = sm_base + static_cast<uint32_t>(L.bw8) * 4u;
   const uint32_t p_base = sm_base + static_cast<uint32_t>(L.p) * 4u;
   const float eps = tb.eps;
+  const bool pow_split = tb.pow_split != 0;
   const float eps_s2 = eps * scale2;
   const float log2_s2 = 2.0f * log2f(scale);
 
@@ -573,7 +598,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
                          static_cast<uint32_t>(warp * ROWS * C) * 4u;
     const float* src = y + ((f0 + warp * ROWS) * static_cast<int64_t>(n) + kc0 + lane) * C;
     const size_t rs = static_cast<size_t>(n) * C;          // row stride in floats (an immediate when N is fixed)
-    if (nf == FT && kcn == 64) {                // whole tile, whole chunk: straight-line copies
+    if (nf == FT && kcn == 64) {                // whole tile, whole 64-filter chunk: straight-line copies
 #pragma unroll
       for (int r = 0; r < ROWS; ++r)
 #pragma unroll
@@ -586,6 +611,16 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
               cp_async<8>(dst + (r * C + c2) * 4 + kk * (TS * 4), src + r * rs + kk * C + c2);
           }
         }
+    } else if (nf == FT && kcn == 32) {         // whole tile, whole 32-filter chunk
+#pragma unroll
+      for (int r = 0; r < ROWS; ++r) {
+        if constexpr (C == 1) {
+          cp_async<4>(dst + r * 4, src + r * rs);
+        } else {
+#pragma unroll
+          for (int c2 = 0; c2 < C; c2 += 2) cp_async<8>(dst + (r * C + c2) * 4, src + r * rs + c2);
+        }
+      }
     } else {
 #pragma unroll 1
       for (int r = 0; r < ROWS; ++r) {
@@ -606,25 +641,43 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
 
   // tiles are walked from the END of the tensor: the producer of y (the forward MDCT) wrote its last ~100 MB into
   // L2 most recently, and the consumer of thr / q (the inverse MDCT) starts at the front, where this kernel ends
+  // Tile scheduling: the first tile of a CTA is its block index, every further one comes from a global ticket
+  // counter (sched[0]) - the CTAs of an SM do not progress at the same rate (the warp schedulers favour the older
+  // ones: measured 18.5 against 21.9 us per tile), and with a static split the SM idles while its slowest CTA
+  // finishes.  A ticket is drawn at the start of a tile and published through shared memory before the barrier of the
+  // tile's last chunk, behind which the first chunk of the next tile is requested.  The last CTA to finish
+  // (sched[1]) re-arms both counters for the next launch.
+  __shared__ long long s_next[2];
   int par = 0;                                  // buffer of the chunk that is processed next
-  if (static_cast<int64_t>(blockIdx.x) < tiles) {
-    const int64_t f0 = (tiles - 1 - blockIdx.x) * FT;
+  int tpar = 0;                                 // parity of the tile (slot of s_next)
+  int64_t tile_i = blockIdx.x;
+  if (tile_i < tiles) {
+    const int64_t f0 = (tiles - 1 - tile_i) * FT;
     load_chunk(f0, static_cast<int>(frames_total - f0 < FT ? frames_total - f0 : FT), 0, 0);
   }
-  for (int64_t tile_i = blockIdx.x; tile_i < tiles; tile_i += gridDim.x) {
+  int slot_i = 0;
+  while (tile_i < tiles) {
     const int64_t tile = tiles - 1 - tile_i;
     const int64_t f0 = tile * FT;
     const int nf = static_cast<int>(frames_total - f0 < FT ? frames_total - f0 : FT);
+    long long ticket = 0;
+    if (tid == 0) ticket = static_cast<long long>(gridDim.x) + atomicAdd(sched, 1u);
+    int64_t next_i = tiles;
 
+    PA_TRACE(slot_i, 0);
     u64 ton_i2 = 0ull, ton_l2 = 0ull;           // tonality sums (psychoacoustic.py:113-116) of the item pair of this lane
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      if (chunk + 1 == n_chunks && tid == 0) s_next[tpar] = ticket;
       cp_async_wait_all();
-      __syncthreads();                          // the chunk has landed; the other buffer (and G in it) is free
+      __syncthreads();                          // the chunk has landed; the other buffer is free
       if (chunk + 1 < n_chunks) {
         load_chunk(f0, nf, chunk + 1, par ^ 1);
-      } else if (tile_i + gridDim.x < tiles) {
-        const int64_t nf0 = (tile - gridDim.x) * FT;
-        load_chunk(nf0, static_cast<int>(frames_total - nf0 < FT ? frames_total - nf0 : FT), 0, par ^ 1);
+      } else {
+        next_i = s_next[tpar];
+        if (next_i < tiles) {
+          const int64_t nf0 = (tiles - 1 - next_i) * FT;
+          load_chunk(nf0, static_cast<int>(frames_total - nf0 < FT ? frames_total - nf0 : FT), 0, par ^ 1);
+        }
       }
       const uint32_t t_lane = t_base + static_cast<uint32_t>(par) * tbuf_bytes + static_cast<uint32_t>(lane) * 8u;
 
@@ -713,19 +766,29 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
           if (jb.w & 0x20000) {
             float ax, ay;
             unpack2(acc2, ax, ay);
-            acc2 = pack2(pow_tab(fmaxf(eps, ax), tb.alpha, s_powa), pow_tab(fmaxf(eps, ay), tb.alpha, s_powa));
+            ax = fmaxf(eps, ax);
+            ay = fmaxf(eps, ay);
+            if (pow_split) {                    // x^alpha = sqrt(x) x^(alpha - 1/2)
+              const u64 e2 = fmul2(pack2(lg2_approx(ax), lg2_approx(ay)), pack2(tb.pow_c1, tb.pow_c1));
+              float ex, ey;
+              unpack2(e2, ex, ey);
+              acc2 = fmul2(pack2(sqrt_approx(ax), sqrt_approx(ay)), pack2(ex2_approx(ex), ex2_approx(ey)));
+            } else {
+              acc2 = pack2(pow_tab(ax, tb.alpha, s_powa), pow_tab(ay, tb.alpha, s_powa));
+            }
           }
           sts_b64(pp, acc2);
         }
       }
       par ^= 1;
     }
-    float* G = sm + L.t + (par ^ 1) * L.tbuf;   // [64][GS] in the buffer of the last chunk; `par` is being filled
+    float* G = sm + L.p;                        // [64][GS] over P and the tonality partials (dead after the MMA loop)
     if (ton_in == nullptr) {
       *reinterpret_cast<u64*>(s_part + warp * TI + 2 * lane) = ton_i2;
       *reinterpret_cast<u64*>(s_part + (kWarps + warp) * TI + 2 * lane) = ton_l2;
     }
     __syncthreads();                            // P and the tonality partials are complete
+    PA_TRACE(slot_i, 1);
 
     // ---- per-item constants of the masking offset (psychoacoustic.py:185-191), once per tile
     if (warp < TI / 32) {
@@ -804,6 +867,24 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       // masking offset, non-linear superposition, quiet threshold            (psychoacoustic.py:185-208, :144)
       const int ma = m0 + g, mb = m0 + g + 8;
       if (ablate & 8) {
+      } else if (!tb.clamp_needed && pow_split) {
+        // acc^(1/alpha) 2^(offset terms) = acc^2 2^((1/alpha - 2) lg2(acc) + offset_log2 offset + log2 scale^2)
+        const float ua = s_u[ma], va = s_v[ma], ub = s_u[mb], vb = s_v[mb];
+        const float c2 = tb.pow_c2;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int j = 32 * nq + 8 * nt + 2 * t;
+          const float2 lin2 = *reinterpret_cast<const float2*>(s_lin + j);
+          const float2 q2 = *reinterpret_cast<const float2*>(s_quiet + j);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float lin = (e & 1) ? lin2.y : lin2.x, qt = (e & 1) ? q2.y : q2.x;
+            const float u = (e & 2) ? ub : ua, v = (e & 2) ? vb : va;
+            const float a = acc[nt][e];
+            const float f = fmaf(c2, lg2_approx(a), fmaf(u, lin, v));
+            G[(j + (e & 1)) * GS + ((e & 2) ? mb : ma)] = fmaxf((a * a) * ex2_approx(f), qt);
+          }
+        }
       } else if (!tb.clamp_needed) {
         const float ua = s_u[ma], va = s_v[ma], ub = s_u[mb], vb = s_v[mb];
         const float inva = tb.inv_alpha;
@@ -843,6 +924,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     }
     __syncthreads();
 
+    PA_TRACE(slot_i, 2);
     // compact side information: the tile's bark-domain thresholds G[band][frame, channel] -> bark_out[frame][band][channel]
     if (tb.bark_out != nullptr) {
 #pragma unroll 1
@@ -994,7 +1076,43 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       }
     }
     // no barrier here: G's buffer and P are next written behind the first barrier of the next tile
+#ifdef AC_PA_TRACE
+    __syncthreads();
+    PA_TRACE(slot_i, 3);
+#endif
+    tile_i = next_i;
+    tpar ^= 1;
+    ++slot_i;
   }
+  if (tid == 0 && atomicAdd(sched + 1, 1u) == gridDim.x - 1) {   // every CTA has drawn its last ticket
+    sched[0] = 0u;
+    sched[1] = 0u;
+  }
+#ifdef AC_PA_TRACE
+  if (threadIdx.x == 0 && g_pa_trace != nullptr) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_pa_trace[static_cast<size_t>(blockIdx.x) * 64] = smid;
+  }
+#endif
+}
+
+#ifdef AC_PA_TRACE
+}  // namespace
+}  // namespace ac
+extern "C" __attribute__((visibility("default"))) int ac_debug_set_pa_trace(unsigned long long* buf) {
+  return static_cast<int>(cudaMemcpyToSymbol(ac::g_pa_trace, &buf, sizeof(buf)));
+}
+namespace ac {
+namespace {
+#endif
+
+// Ticket counters of the tile scheduler: a ring of {next ticket, finished CTAs} pairs owned by the plan (zeroed at
+// creation, re-armed by the last CTA of every launch); launches take the slots round robin, so launches of one plan
+// that overlap on different streams do not share a counter (up to kPaSchedSlots in flight)
+unsigned* pa_sched_slot(const PaDeviceTables& tb) {
+  static std::atomic<unsigned> next{0};
+  return tb.sched + 2 * (next.fetch_add(1, std::memory_order_relaxed) % kPaSchedSlots);
 }
 
 int mma_sm_count() {
@@ -1010,28 +1128,39 @@ int mma_sm_count() {
   return cached;
 }
 
-template <int C, bool QUANT, int NFIX>
-cudaError_t launch_mma_tile_n(const PaDeviceTables& tb, const float* y, const float* ton_in, float omd, float thr_scale,
-                              float* thr_out, int32_t* q_out, int64_t frames, cudaStream_t stream) {
+template <int C, bool QUANT, int NFIX, int MINB>
+cudaError_t launch_mma_tile_nb(const PaDeviceTables& tb, const float* y, const float* ton_in, float omd, float thr_scale,
+                               float* thr_out, int32_t* q_out, int64_t frames, int per_sm, cudaStream_t stream) {
   constexpr int FT = kTI / C;
   const size_t smem = static_cast<size_t>(layout2(tb).total) * sizeof(float);
   const int64_t tiles = (frames + FT - 1) / FT;
-  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
-  per_sm = per_sm > 3 ? 3 : (per_sm < 1 ? 1 : per_sm);
-  if (const char* e = std::getenv("AC_PA_CTAS")) per_sm = std::max(1, std::min(per_sm, std::atoi(e)));   // experiments
   const int64_t cap = static_cast<int64_t>(mma_sm_count()) * per_sm;
   const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
   int ablate = 0;
   // experiments (profiles/README.md, ablation table): bit 0 skips the tonality pass, 1 the band sums, 2 the MMA loop,
   // 3 its epilogue, 4 phase D, 5 the asynchronous copies of y - the results are then wrong, only the time is of interest
   if (const char* e = std::getenv("AC_PA_ABLATE")) ablate = std::atoi(e);
-  auto kernel = pa_mma_tile_kernel<C, QUANT, NFIX>;
+  auto kernel = pa_mma_tile_kernel<C, QUANT, NFIX, MINB>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
   kernel<<<grid, kThreads, smem, stream>>>(tb, *tb.jobs_host, y, ton_in, omd, thr_scale, thr_out, q_out, frames, tiles,
-                                           ablate);
+                                           pa_sched_slot(tb), ablate);
   count_launch();
   return cudaGetLastError();
+}
+
+// CTAs per SM: four when the shared memory of the plan allows it (32-filter chunks; the kernel is then compiled for 64
+// registers), else three
+template <int C, bool QUANT, int NFIX>
+cudaError_t launch_mma_tile_n(const PaDeviceTables& tb, const float* y, const float* ton_in, float omd, float thr_scale,
+                              float* thr_out, int32_t* q_out, int64_t frames, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(layout2(tb).total) * sizeof(float);
+  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  per_sm = per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm);
+  if (const char* e = std::getenv("AC_PA_CTAS")) per_sm = std::max(1, std::min(per_sm, std::atoi(e)));   // experiments
+  if (per_sm >= 4)
+    return launch_mma_tile_nb<C, QUANT, NFIX, 4>(tb, y, ton_in, omd, thr_scale, thr_out, q_out, frames, per_sm, stream);
+  return launch_mma_tile_nb<C, QUANT, NFIX, 3>(tb, y, ton_in, omd, thr_scale, thr_out, q_out, frames, per_sm, stream);
 }
 
 // filters_n of the headline configurations are compile-time values (row strides become immediates)

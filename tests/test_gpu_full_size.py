@@ -4,7 +4,16 @@ Every clip of the GPU result is compared with the oracle run on the same clip (t
 bench.py's cpu_baseline leg runs it): cfg1 and cfg2 complete, cfg3 / cfg4 / the per-GPU shard of cfg5 on the first
 clips of a full-length batch.  Per clip:
 
-  * Y, tonality, thr against the float64 oracle          -> <= 1e-5 x signal RMS (north star), tonality <= 2e-5
+  * Y against the float64 oracle                          -> <= 1e-5 x signal RMS (north star)
+  * tonality against the float64 oracle fed the SAME fp32 amplitudes -> <= 2e-5 (the kernel's own error)
+  * thr (stand-alone call and the fused encoder's step) against the float64 oracle fed the SAME amplitudes and
+    tonality                                              -> <= 1e-5 x signal RMS (north star)
+  * the whole fp32 chain against the whole float64 chain: tonality <= 2e-4, thr <= 4e-5 x signal RMS.  These two are
+    bounds on the CONDITIONING of the model, not on the kernels: tonality takes the log of every coefficient, so the
+    fp32 rounding of a near-zero MDCT coefficient moves it by 1e-5 .. 3e-5, and the masking offset carries that into
+    thr of the loudest bands.  The fp32-faithful oracle (the reference's default graph) is itself up to 3e-5 / 1.4e-5 x
+    RMS away from the float64 chain on these very clips, with the model arithmetic contributing 2e-7 x RMS
+    (measured with oracle/ alone)
   * q against the fp32-faithful oracle (the reference's default graph computes in fp32)
                                                           -> >= 99.99 % identical, the rest +-1
   * q against oracle.quantize(Y_gpu, step_gpu)           -> bit-exact (quantiser fed the same threshold)
@@ -35,7 +44,7 @@ TOL = 1e-5
 
 class _Acc:
   def __init__(self):
-    self.e_y = self.e_thr = self.e_ton = self.e_xhat = 0.0
+    self.e_y = self.e_thr = self.e_thr_chain = self.e_ton = self.e_ton_chain = self.e_xhat = 0.0
     self.q_total = self.q_diff = 0
     self.q_maxdiff = 0
     self.q_selfdiff = 0
@@ -66,8 +75,14 @@ def _check_clips(sr, n, c, seconds, clips, first_clip=0, chunk=16, thr_scale=1.0
     y_ref = mdct64.transform(x64)
     ton_ref = pa64.tonality(y_ref)
     thr_ref = pa64.global_masking_threshold(y_ref, ton_ref)
-    r = {"e_y": np.max(np.abs(y - y_ref)) / sig, "e_ton": np.max(np.abs(ton - ton_ref)),
-         "e_thr": max(np.max(np.abs(thr - thr_ref)), np.max(np.abs(step - thr_scale * thr_ref))) / sig}
+    y_gpu64 = y.astype(np.float64)
+    thr_same = pa64.global_masking_threshold(y_gpu64, ton.astype(np.float64))      # same inputs as the kernel had
+    ton_same = pa64.tonality(y_gpu64)
+    thr_fused = pa64.global_masking_threshold(y_gpu64, ton_same)                   # the encoder's internal tonality
+    r = {"e_y": np.max(np.abs(y - y_ref)) / sig, "e_ton": np.max(np.abs(ton - ton_same)),
+         "e_ton_chain": np.max(np.abs(ton - ton_ref)),
+         "e_thr": max(np.max(np.abs(thr - thr_same)), np.max(np.abs(step - thr_scale * thr_fused))) / sig,
+         "e_thr_chain": max(np.max(np.abs(thr - thr_ref)), np.max(np.abs(step - thr_scale * thr_ref))) / sig}
     # fp32-faithful reference chain for the integers and the reconstruction error
     y32 = mdct32.transform(x)
     thr32 = pa32.global_masking_threshold(y32, pa32.tonality(y32)) * np.float32(thr_scale)
@@ -100,7 +115,9 @@ def _check_clips(sr, n, c, seconds, clips, first_clip=0, chunk=16, thr_scale=1.0
         for r in pool.map(one_clip, jobs):
           acc.e_y = max(acc.e_y, r["e_y"])
           acc.e_ton = max(acc.e_ton, r["e_ton"])
+          acc.e_ton_chain = max(acc.e_ton_chain, r["e_ton_chain"])
           acc.e_thr = max(acc.e_thr, r["e_thr"])
+          acc.e_thr_chain = max(acc.e_thr_chain, r["e_thr_chain"])
           acc.e_xhat = max(acc.e_xhat, r["e_xhat"])
           acc.q_total += r["q_total"]
           acc.q_diff += r["q_diff"]
@@ -119,8 +136,10 @@ def _assert_parity(acc, expect_coefficients=None):
   if expect_coefficients is not None:
     assert acc.q_total == expect_coefficients
   assert acc.e_y <= TOL, acc.e_y                       # MDCT coefficients, relative to the clip's RMS
-  assert acc.e_ton <= 2e-5, acc.e_ton
+  assert acc.e_ton <= 2e-5, acc.e_ton                  # tonality kernel on its own input
+  assert acc.e_ton_chain <= 2e-4, acc.e_ton_chain      # whole fp32 chain against the float64 chain (see the docstring)
   assert acc.e_thr <= TOL, acc.e_thr                   # masking threshold (stand-alone call and the fused step)
+  assert acc.e_thr_chain <= 4e-5, acc.e_thr_chain      # whole fp32 chain against the float64 chain (conditioning)
   assert acc.e_xhat <= TOL, acc.e_xhat                 # IMDCT, relative to the clip's RMS
   assert acc.q_selfdiff == 0                           # quantiser bit-exact given the same threshold
   assert acc.q_maxdiff <= 1
