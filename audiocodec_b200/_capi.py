@@ -48,6 +48,9 @@ SIGNATURES = {
                                               _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
   "ac_pa_expand_threshold_f32": (ctypes.c_int, [_c_void_p, _c_void_p, ctypes.c_float, _c_void_p, _c_int64, _c_int64,
                                                 ctypes.c_int, _c_void_p]),
+  "ac_codec_encode_workspace_bytes": (_c_int64, [_c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int]),
+  "ac_codec_encode_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, ctypes.c_float, ctypes.c_float, _c_void_p,
+                                         _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p, _c_void_p]),
   "ac_pa_add_noise_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, ctypes.c_uint64, _c_void_p]),
   "ac_quantize_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
   "ac_dequantize_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),

@@ -10,6 +10,7 @@ import ctypes
 import torch
 
 from . import _capi
+from ._tensors import adopt, stream_ptr
 from .mdctransformer import MDCTransformer
 from .psychoacoustic import PsychoacousticModel
 
@@ -22,9 +23,49 @@ class AudioCodec:
     self.psychoacoustic = PsychoacousticModel(sample_rate, filter_bands_n=filters_n, bark_bands_n=bark_bands_n, alpha=alpha)
     self._pipes = {}
 
-  def encode(self, x, drown=0.0, thr_scale=1.0):
-    """x [B, S, C] -> (q int32 [B, S/N + 1, N, C], step float32 same shape)."""
-    return self.psychoacoustic.encode(self.mdct.transform(x), drown=drown, thr_scale=thr_scale)
+  def encode(self, x, drown=0.0, thr_scale=1.0, compact=False, return_threshold=True):
+    """x [B, S, C] -> (q int32 [B, S/N + 1, N, C], step float32 same shape).
+
+    One call of the library's single-pass encoder (ac_codec_encode_f32): for stereo signals with filters_n = 256 the
+    forward MDCT, the masking model and the quantiser run in ONE kernel and the amplitudes never reach global memory;
+    other shapes run transform + encode through a scratch tensor.  Bit-identical to
+    psychoacoustic.encode(mdct.transform(x)) either way.  compact=True returns the bark-domain thresholds
+    [B, S/N + 1, 64, C] instead of the steps (decode with decode_compact); return_threshold=False returns q alone.
+    """
+    xt, back = adopt(x, "x")
+    if xt.dim() != 3:
+      raise ValueError("x must be [batches_n, samples_n, channels_n]")
+    b, s, c = xt.shape
+    n = self.filters_n
+    if s % n != 0:
+      raise ValueError(f"samples_n ({s}) must be a multiple of filters_n ({n})")
+    frames = s // n + 1
+    dev = xt.device
+    lib = _capi.lib()
+    with torch.cuda.device(dev):
+      mplan, pplan = self.mdct._plan(dev), self.psychoacoustic._plan(dev)
+      q = torch.empty((b, frames, n, c), dtype=torch.int32, device=dev)
+      side = None
+      if compact:
+        side = torch.empty((b, frames, 64, c), dtype=torch.float32, device=dev)
+      elif return_threshold:
+        side = torch.empty((b, frames, n, c), dtype=torch.float32, device=dev)
+      need = lib.ac_codec_encode_workspace_bytes(mplan, pplan, b, s, c)
+      if need < 0:
+        raise ValueError("invalid shape for the encoder")
+      work = torch.empty(need // 4, dtype=torch.float32, device=dev) if need > 0 else None
+      _capi.check(lib.ac_codec_encode_f32(
+        mplan, pplan, xt.data_ptr(), float(drown), float(thr_scale),
+        side.data_ptr() if (side is not None and not compact) else None,
+        side.data_ptr() if compact else None, q.data_ptr(), b, s, c,
+        work.data_ptr() if work is not None else None, stream_ptr(dev)))
+    if side is None:
+      return back(q)
+    return back(q), back(side)
+
+  def decode_compact(self, q, bark_thr, thr_scale=1.0):
+    """(q, bark-domain thresholds of encode(compact=True)) -> x_hat; the steps are rebuilt inside the inverse MDCT."""
+    return self.mdct.inverse_transform_compact(q, bark_thr, self.psychoacoustic, thr_scale=thr_scale)
 
   def decode(self, q, step):
     """(q, step) -> x_hat [B, S + 2 N, C]; x_hat[:, N:-N] reconstructs x (one-block delay, mdctransformer.py:156)."""

@@ -774,6 +774,57 @@ int ac_pa_expand_threshold_f32(const ac_pa_plan* plan, const float* bark_thr, fl
   return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_expand_threshold launch");
 }
 
+// ----------------------------------------------------------------------------------- single-pass encoder
+int64_t ac_codec_encode_workspace_bytes(const ac_mdct_plan* mdct, const ac_pa_plan* pa, int64_t batches, int64_t samples,
+                                        int channels) {
+  if (mdct == nullptr || pa == nullptr || batches < 0 || samples < 0 || channels < 1) return -1;
+  const int n = mdct->tb.n;
+  if (samples % n != 0) return -1;
+  if (ac::pa_encode_fused_supported(pa->tb, mdct->tb, channels)) return 0;
+  return batches * (samples / n + 1) * n * channels * static_cast<int64_t>(sizeof(float));
+}
+
+int ac_codec_encode_f32(const ac_mdct_plan* mdct, const ac_pa_plan* pa, const float* x, float drown, float thr_scale,
+                        float* step_out, float* bark_thr_out, int32_t* q, int64_t batches, int64_t samples, int channels,
+                        void* workspace, void* stream) {
+  if (int rc = check_common(mdct, batches, samples, channels)) return rc;
+  if (int rc = check_common(pa, batches, samples, channels)) return rc;
+  const int n = mdct->tb.n;
+  if (pa->tb.n != n) return fail(AC_ERR_INVALID, "the two plans have different filters_n (%d, %d)", n, pa->tb.n);
+  if (samples % n != 0)
+    return fail(AC_ERR_INVALID, "samples_n (%lld) must be a multiple of filters_n (%d)", (long long)samples, n);
+  if (!(thr_scale > 0.f)) return fail(AC_ERR_INVALID, "thr_scale must be positive");
+  const int64_t blocks = samples / n;
+  if (blocks + 1 > 2147483647LL / 2) return fail(AC_ERR_INVALID, "too many blocks per batch row");
+  if (batches == 0) return AC_OK;
+  if ((x == nullptr && samples > 0) || q == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  if (!aligned16(x) || !aligned16(q) || !aligned16(step_out) || !aligned16(bark_thr_out) || !aligned16(workspace))
+    return fail(AC_ERR_INVALID, "all tensors must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (ac::pa_encode_fused_supported(pa->tb, mdct->tb, channels)) {
+    cudaError_t err = ac::pa_encode_fused(pa->tb, mdct->tb, x, drown, thr_scale, step_out, bark_thr_out, q, batches, blocks,
+                                          channels, st);
+    return err == cudaSuccess ? AC_OK : cuda_fail(err, "fused encoder launch");
+  }
+  // other shapes: transform into the caller's workspace, then the masking / quantising kernel
+  if (workspace == nullptr) return fail(AC_ERR_INVALID, "this shape needs a workspace (ac_codec_encode_workspace_bytes)");
+  float* y = static_cast<float*>(workspace);
+  cudaError_t err = ac::mdct_forward(mdct->tb, x, y, batches, blocks, channels, st);
+  if (err != cudaSuccess) return cuda_fail(err, "mdct_forward launch");
+  const int64_t rows = batches * (blocks + 1);
+  if (bark_thr_out != nullptr) {
+    if (!ac::pa_mma_tile_supported(pa->tb, channels))
+      return fail(AC_ERR_UNSUPPORTED, "compact side information needs bark_bands_n == 64, <= 3 bands per filter, 1/2/4 channels");
+    ac::PaDeviceTables with_out = pa->tb;
+    with_out.bark_out = bark_thr_out;
+    err = ac::pa_threshold_mma_tile(with_out, y, nullptr, static_cast<float>(1.0 - static_cast<double>(drown)), thr_scale,
+                                    step_out, q, rows, channels, st);
+  } else {
+    err = ac::pa_threshold(pa->tb, y, nullptr, drown, thr_scale, step_out, q, rows, channels, st);
+  }
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_encode launch");
+}
+
 int ac_pa_add_noise_f32(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, void* stream) {
   if (n < 0) return fail(AC_ERR_INVALID, "negative size");
   if (n == 0) return AC_OK;

@@ -122,6 +122,14 @@ cudaError_t pa_threshold_mma_tile(const PaDeviceTables& tb, const float* y, cons
                                   float thr_scale, float* thr_out, int32_t* q_out, int64_t frames, int channels,
                                   cudaStream_t stream);
 
+// psycho_mma_kernels.cu, single-pass encoder: forward MDCT + masking + quantiser in one kernel,
+// x [B, S, 2] -> q (and the steps thr_out and / or the bark-domain thresholds bark_out, either may be null); the
+// amplitudes never reach global memory.  Stereo, filters_n = 256; cudaErrorNotSupported otherwise.
+bool pa_encode_fused_supported(const PaDeviceTables& tb, const MdctDeviceTables& mt, int channels);
+cudaError_t pa_encode_fused(const PaDeviceTables& tb, const MdctDeviceTables& mt, const float* x, float drown,
+                            float thr_scale, float* thr_out, float* bark_out, int32_t* q_out, int64_t batches,
+                            int64_t blocks_n, int channels, cudaStream_t stream);
+
 // float64 compute dtype (f64_kernels.cu): the same tables in double, sparse forms shared with the fp32 plan
 struct MdctDeviceTables64 {
   int n = 0;

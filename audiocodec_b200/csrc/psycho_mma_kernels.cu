@@ -30,6 +30,8 @@
 // y is read from HBM by the copies and again (an L2 hit) in D: HBM sees one read of y and one write each of thr and q.
 // tools/emulate_pa_mma.py checks the fragment / swizzle index maps on the CPU; profiles/README.md has the measurements.
 #include "kernels.h"
+#include "async_copy.cuh"
+#include "mdct_tile_core.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -155,15 +157,17 @@ struct Layout2 {
   int powa, powia, t, tbuf, p, part, uv, sfh, sfl, quiet, lin, bw8, filt4, total;
 };
 
-__host__ __device__ inline Layout2 layout2(const PaDeviceTables& tb) {
+// fused: the single-pass encoder (x -> q): T holds ALL filters of the tile's frames (the forward MDCT leaves them
+// there, transposed) instead of two chunk buffers
+__host__ __device__ inline Layout2 layout2(const PaDeviceTables& tb, const bool fused = false) {
   Layout2 L;
   const int kc = tb.n < tb.mma_chunk_k ? tb.n : tb.mma_chunk_k;
-  const int t_rows = (kc + 3) * kTS;                    // 3 zero rows behind the chunk for the 4-filter steps
+  const int t_rows = ((fused ? tb.n : kc) + 3) * kTS;   // 3 zero rows behind the chunk for the 4-filter steps
   int o = 0;
   L.powa = o;    o += 512;                              // the exponent tables come first: an index with the sign bit
   L.powia = o;   o += 512;                              //   set (NaN input) still reads inside the allocation
   L.tbuf = (t_rows + 3) & ~3;
-  L.t = o;       o += 2 * L.tbuf;                       // two chunk buffers: one is filled while the other is read
+  L.t = o;       o += (fused ? 1 : 2) * L.tbuf;         // two chunk buffers: one is filled while the other is read
   // G [64][kGS] aliases P and the tonality partials behind it: both are dead once the MMA loop and the per-item
   // constants are done, and are next written behind the first barrier of the next tile
   static_assert(kNB * kPS + 2 * kWarps * kTI >= kNB * kGS, "G must fit into P + the tonality partials");
@@ -411,11 +415,12 @@ __device__ __forceinline__ void phase_d_unit_mono2(const float4* __restrict__ fi
 // the filter-table entry, the slot-pattern branch and the address of the band rows of G (pair h's items sit 2 h floats
 // further), and their dependency chains interleave: fewer shared-memory wavefronts and control instructions per
 // coefficient than one pair at a time.  row_stride in floats; yv[h][i] = the pair's two amplitudes of filter 32 i + lane.
-template <int C, bool QUANT, bool THR, bool FILT_SMEM, int KI, int R>
+// GUARD: pair h is stored only when h < pairs_live (ragged last tile of the fused encoder).
+template <int C, bool QUANT, bool THR, bool FILT_SMEM, int KI, int R, bool GUARD = false>
 __device__ __forceinline__ void phase_d_unit_pairs(const float4* __restrict__ filt4, const unsigned masks,
                                                     const float2 (&yv)[R][KI], float* __restrict__ t0,
                                                     int32_t* __restrict__ q0, const size_t row_stride, const float* gr,
-                                                    const float eps_s2) {
+                                                    const float eps_s2, const int pairs_live = R) {
   constexpr int GS = kGS;
   const u64 k_neg = pack2(-1.f, -1.f);
 #pragma unroll
@@ -445,6 +450,7 @@ __device__ __forceinline__ void phase_d_unit_pairs(const float4* __restrict__ fi
     }
 #pragma unroll
     for (int h = 0; h < R; ++h) {
+      if (GUARD && h >= pairs_live) break;
       float vx, vy;
       unpack2(v[h], vx, vy);
       vx = fmaxf(eps_s2, vx);
@@ -495,20 +501,28 @@ __device__ __forceinline__ void pa_trace(int slot, int ev) {
 #define PA_TRACE(slot, ev)
 #endif
 
-template <int C, bool QUANT, int NFIX, int MINB>
+// FUSED (the single-pass encoder; stereo, filters_n = 256): `y` is the SIGNAL x [B, S, 2].  A tile is
+// 32 consecutive frames of one batch row: their 33 blocks arrive by one bulk copy, the forward MDCT of
+// mdct_forward_tile_kernel (mdctransformer.py:61-125) runs in place on the block rows and its post-twiddle stores the
+// amplitudes TRANSPOSED into the same region (T[filter][item], all filters resident) once every group has finished its
+// FFT exchanges - Y never goes to global memory.  The phases below then read T exactly like a chunk buffer, phase D
+// takes its amplitudes from T instead of L2, and the next tile's blocks are requested when phase D is done.
+template <int C, bool QUANT, int NFIX, int MINB, bool FUSED = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_constant__ PaJobParams jp,
                    const float* __restrict__ y, const float* __restrict__ ton_in, float one_minus_drown, float thr_scale,
                    float* __restrict__ thr_out, int32_t* __restrict__ q_out, int64_t frames_total, int64_t tiles,
-                   unsigned* __restrict__ sched, const int ablate) {
+                   unsigned* __restrict__ sched, const int ablate, const MdctDeviceTables mt, const int blocks_n,
+                   const int tiles_per_row) {
   using VF = typename Vec<C>::F;
   using VI = typename Vec<C>::I;
   constexpr int TI = kTI, TS = kTS, GS = kGS, PS = kPS;
   constexpr int FT = TI / C;                    // frames per tile
   constexpr int ROWS = FT / kWarps;             // frame rows per warp
   static_assert(FT % kWarps == 0, "tile shape");
-  extern __shared__ __align__(16) float sm[];
-  const Layout2 L = layout2(tb);
+  static_assert(!FUSED || (C == 2 && NFIX == 256), "the fused encoder is built for stereo, filters_n = 256");
+  extern __shared__ __align__(128) float sm[];
+  const Layout2 L = layout2(tb, FUSED);
   const int n = NFIX > 0 ? NFIX : tb.n, kc = n < tb.mma_chunk_k ? n : tb.mma_chunk_k;
   const int n_chunks = tb.mma_n_chunks;
   float2* s_powa = reinterpret_cast<float2*>(sm + L.powa);
@@ -575,6 +589,21 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     }
   }
 
+  // the three zero rows behind a whole chunk are never written by the copies: zeroed once, in both buffers (a short
+  // last chunk zeroes its own rows in load_chunk; the barriers of the chunk loop order these stores before any read)
+  if constexpr (FUSED) {
+    for (int i = tid; i < 3 * TS; i += kThreads) sm[L.t + n * TS + i] = 0.f;   // behind the last filter; never overwritten
+  } else {
+    for (int i = tid; i < 2 * 3 * TS; i += kThreads)
+      sm[L.t + (i / (3 * TS)) * L.tbuf + kc * TS + (i % (3 * TS))] = 0.f;
+  }
+  __shared__ __align__(8) uint64_t s_mbar;     // FUSED: completion of the tile's bulk copy
+  if (FUSED && tid == 0) {
+    mbar_init(&s_mbar, 1);
+    mbar_fence_init();
+  }
+  if constexpr (FUSED) __syncthreads();
+
   const uint32_t sm_base = static_cast<uint32_t>(__cvta_generic_to_shared(sm));
   const uint32_t t_base = sm_base + static_cast<uint32_t>(L.t) * 4u;
   const uint32_t tbuf_bytes = static_cast<uint32_t>(L.tbuf) * 4u;
@@ -592,8 +621,10 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     if (ablate & 32) return;
     const int kc0 = chunk * tb.mma_chunk_k;
     const int kcn = (n - kc0 < kc ? n - kc0 : kc);
-    float* tz = sm + L.t + buf * L.tbuf + kcn * TS;
-    for (int i = tid; i < 3 * TS; i += kThreads) tz[i] = 0.f;
+    if (kcn != kc) {                            // a short last chunk: its zero rows sit inside the data rows of the others
+      float* tz = sm + L.t + buf * L.tbuf + kcn * TS;
+      for (int i = tid; i < 3 * TS; i += kThreads) tz[i] = 0.f;
+    }
     const uint32_t dst = t_base + static_cast<uint32_t>(buf) * tbuf_bytes + static_cast<uint32_t>(lane) * (TS * 4u) +
                          static_cast<uint32_t>(warp * ROWS * C) * 4u;
     const float* src = y + ((f0 + warp * ROWS) * static_cast<int64_t>(n) + kc0 + lane) * C;
@@ -651,26 +682,119 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   int par = 0;                                  // buffer of the chunk that is processed next
   int tpar = 0;                                 // parity of the tile (slot of s_next)
   int64_t tile_i = blockIdx.x;
+  // FUSED: the blocks f0l - 1 .. f0l + FT - 1 of batch row b -> rows 0 .. FT of the T region (2 KB each, as in
+  // mdct_forward_tile_kernel); rows outside the signal are zero-filled by the consumer.  Thread 0 only.
+  const int frames_row = blocks_n + 1;          // FUSED: frames per batch row
+  auto issue_x_load = [&](int64_t ti) {
+    if constexpr (FUSED) {
+      constexpr int ROWF = 256 * C;             // floats per block row
+      const int64_t tile = tiles - 1 - ti;
+      const int64_t b = tile / tiles_per_row;
+      const int f0l = static_cast<int>(tile - b * tiles_per_row) * FT;
+      const int r_lo = f0l == 0 ? 1 : 0;
+      const int r_hi = min(FT + 1, blocks_n - f0l + 1);
+      if (r_hi > r_lo) {
+        const uint32_t bytes = static_cast<uint32_t>(r_hi - r_lo) * ROWF * sizeof(float);
+        mbar_arrive_expect_tx(&s_mbar, bytes);
+        bulk_load(sm + L.t + r_lo * ROWF, y + (b * blocks_n + (f0l - 1 + r_lo)) * static_cast<int64_t>(ROWF), bytes, &s_mbar);
+      } else {
+        mbar_arrive(&s_mbar);
+      }
+    }
+  };
   if (tile_i < tiles) {
-    const int64_t f0 = (tiles - 1 - tile_i) * FT;
-    load_chunk(f0, static_cast<int>(frames_total - f0 < FT ? frames_total - f0 : FT), 0, 0);
+    if constexpr (FUSED) {
+      if (tid == 0) issue_x_load(tile_i);
+    } else {
+      const int64_t f0 = (tiles - 1 - tile_i) * FT;
+      load_chunk(f0, static_cast<int>(frames_total - f0 < FT ? frames_total - f0 : FT), 0, 0);
+    }
   }
   int slot_i = 0;
   while (tile_i < tiles) {
     const int64_t tile = tiles - 1 - tile_i;
-    const int64_t f0 = tile * FT;
-    const int nf = static_cast<int>(frames_total - f0 < FT ? frames_total - f0 : FT);
+    int64_t f0;                                 // first frame of the tile in the flattened [B F] frame axis
+    int nf;                                     // frames of the tile inside the tensor
+    if constexpr (FUSED) {
+      const int64_t b = tile / tiles_per_row;
+      const int f0l = static_cast<int>(tile - b * tiles_per_row) * FT;
+      f0 = b * frames_row + f0l;
+      nf = min(FT, frames_row - f0l);
+    } else {
+      f0 = tile * FT;
+      nf = static_cast<int>(frames_total - f0 < FT ? frames_total - f0 : FT);
+    }
     long long ticket = 0;
     if (tid == 0) ticket = static_cast<long long>(gridDim.x) + atomicAdd(sched, 1u);
     int64_t next_i = tiles;
+
+    if constexpr (FUSED) {
+      // ---- forward MDCT of the tile's frames, in place (mdct_forward_tile_kernel with 32 groups of 8 threads)
+      using Plan = Plan256;
+      constexpr int M = Plan::M, N = 2 * M, H = M, T = Plan::T, E = Plan::E, R0 = Plan::R0, ROWF = N * C;
+      static_assert(kThreads / T == FT, "one group of threads per frame");
+      const int64_t b = tile / tiles_per_row;
+      const int f0l = static_cast<int>(tile - b * tiles_per_row) * FT;
+      const int g = tid / T, t = tid % T, variant = (tid >> 3) & 1;
+      float* buf = sm + L.t;
+      float* prev = buf + g * ROWF;             // block row before this group's frame
+      float* cur = prev + ROWF;                 // the frame's own block: input, FFT scratch
+      const int r_lo = f0l == 0 ? 1 : 0;
+      const int r_hi = min(FT + 1, blocks_n - f0l + 1);
+      mbar_wait(&s_mbar, slot_i & 1);
+      if (r_lo > 0 || r_hi < FT + 1) {          // blocks outside the signal are zero (mdctransformer.py:366)
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r_lo > 0)
+          for (int i = tid * 4; i < ROWF; i += kThreads * 4) *reinterpret_cast<float4*>(buf + i) = z;
+        for (int i = max(r_hi, r_lo) * ROWF + tid * 4; i < (FT + 1) * ROWF; i += kThreads * 4)
+          *reinterpret_cast<float4*>(buf + i) = z;
+        __syncthreads();
+      }
+      float2 v0[E], v1[E];
+#pragma unroll
+      for (int s = 0; s < E; ++s) {             // window + fold + pre-twiddle (mdctransformer.py:118, H)
+        const int nn = Plan::in_index(t, s);
+        constexpr int kHalf = R0 / 2;
+        const bool low = (s % R0) < kHalf;
+        const int p = low ? H - 1 - 2 * nn : 2 * nn - H;
+        const int a1 = variant ? N - 1 - p : p;
+        const int a2 = (N - 1) - a1;
+        const float2 l0 = ld2<C, ROWF>(prev, a1), l1 = ld2<C, ROWF>(prev, a2);
+        const float2 l2 = ld2<C, ROWF>(cur, a1), l3 = ld2<C, ROWF>(cur, a2);
+        const float4 kr = __ldg(&mt.pre_fwd[(variant * 2) * M + nn]);
+        const float4 ki = __ldg(&mt.pre_fwd[(variant * 2 + 1) * M + nn]);
+        v0[s].x = fmaf(l3.x, kr.w, fmaf(l2.x, kr.z, fmaf(l1.x, kr.y, l0.x * kr.x)));
+        v0[s].y = fmaf(l3.x, ki.w, fmaf(l2.x, ki.z, fmaf(l1.x, ki.y, l0.x * ki.x)));
+        v1[s].x = fmaf(l3.y, kr.w, fmaf(l2.y, kr.z, fmaf(l1.y, kr.y, l0.y * kr.x)));
+        v1[s].y = fmaf(l3.y, ki.w, fmaf(l2.y, ki.z, fmaf(l1.y, ki.y, l0.y * ki.x)));
+      }
+      __syncthreads();                          // every block row has been read: the rows become FFT scratch
+      fft2<Plan>(v0, v1, reinterpret_cast<float4*>(cur), t, g, mt.tw_pass1, mt.tw_pass2);
+      __syncthreads();                          // every exchange is over: the region becomes T[filter][item]
+      float* tcol = buf + 2 * g;                // items 2 g, 2 g + 1 = the two channels of frame g
+#pragma unroll
+      for (int s = 0; s < E; ++s) {             // post-twiddle; bin k -> filters 2k and N-1-2k
+        const int k = Plan::out_index(t, s);
+        const float4 c4 = __ldg(&mt.post_fwd[variant * M + k]);
+        const int i1 = variant ? N - 1 - 2 * k : 2 * k;
+        const int i2 = (N - 1) - i1;
+        *reinterpret_cast<float2*>(tcol + i1 * TS) =
+            make_float2(fmaf(v0[s].y, c4.y, v0[s].x * c4.x), fmaf(v1[s].y, c4.y, v1[s].x * c4.x));
+        *reinterpret_cast<float2*>(tcol + i2 * TS) =
+            make_float2(fmaf(v0[s].y, c4.w, v0[s].x * c4.z), fmaf(v1[s].y, c4.w, v1[s].x * c4.z));
+      }
+      // no barrier here: the first barrier of the chunk loop follows
+    }
 
     PA_TRACE(slot_i, 0);
     u64 ton_i2 = 0ull, ton_l2 = 0ull;           // tonality sums (psychoacoustic.py:113-116) of the item pair of this lane
     for (int chunk = 0; chunk < n_chunks; ++chunk) {
       if (chunk + 1 == n_chunks && tid == 0) s_next[tpar] = ticket;
-      cp_async_wait_all();
+      if constexpr (!FUSED) cp_async_wait_all();
       __syncthreads();                          // the chunk has landed; the other buffer is free
-      if (chunk + 1 < n_chunks) {
+      if constexpr (FUSED) {                    // (T complete / the P partials of the previous chunk are visible)
+        if (chunk + 1 == n_chunks) next_i = s_next[tpar];
+      } else if (chunk + 1 < n_chunks) {
         load_chunk(f0, nf, chunk + 1, par ^ 1);
       } else {
         next_i = s_next[tpar];
@@ -679,7 +803,8 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
           load_chunk(nf0, static_cast<int>(frames_total - nf0 < FT ? frames_total - nf0 : FT), 0, par ^ 1);
         }
       }
-      const uint32_t t_lane = t_base + static_cast<uint32_t>(par) * tbuf_bytes + static_cast<uint32_t>(lane) * 8u;
+      const uint32_t t_lane = FUSED ? t_base + static_cast<uint32_t>(chunk * tb.mma_chunk_k) * (TS * 4u) + static_cast<uint32_t>(lane) * 8u
+                                    : t_base + static_cast<uint32_t>(par) * tbuf_bytes + static_cast<uint32_t>(lane) * 8u;
 
       // ---- A1: tonality sums over this warp's share of the filters: sum I and sum log2 max(eps, I)   (:113, :312)
       // two filters per logarithm: log2 a + log2 b = log2(a b), a b >= eps^2 (finite for |y| < 1e9)
@@ -942,7 +1067,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       const bool thr = thr_out != nullptr;
       constexpr int KI = C == 4 ? 4 : 8;
       const int rows_live = (ablate & 16) ? 0 : min(ROWS, nf - warp * ROWS);
-      const bool whole = C <= 2 && n % 64 == 0 && rows_live == ROWS;   // the common case, see below
+      const bool whole = C <= 2 && n % 64 == 0 && (FUSED || rows_live == ROWS);   // the common case, see below
       if (C == 1 && n % (32 * KI) == 0 && !whole) {
         // mono: pairs of consecutive rows on the packed path (phase_d_unit_mono2)
         if constexpr (C == 1) {
@@ -996,7 +1121,13 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
               const int k0 = u * (32 * K2);
               const int64_t off = off0 + C * k0;
               float2 yv[R][K2];
-              if (QUANT) {                      // an L2 hit; loading a unit ahead changes nothing (measured)
+              if constexpr (FUSED) {            // the amplitudes are still in T[filter][item]
+                const float* tp = sm + L.t + (k0 + lane) * TS + (warp * ROWS + r0) * C;
+#pragma unroll
+                for (int h = 0; h < R; ++h)
+#pragma unroll
+                  for (int i = 0; i < K2; ++i) yv[h][i] = *reinterpret_cast<const float2*>(tp + 32 * i * TS + 2 * h);
+              } else if (QUANT) {               // an L2 hit; loading a unit ahead changes nothing (measured)
 #pragma unroll
                 for (int h = 0; h < R; ++h)
 #pragma unroll
@@ -1011,8 +1142,9 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
               unsigned masks = 0;
 #pragma unroll
               for (int i = 0; i < K2; ++i) masks |= static_cast<unsigned>(tb.filt_mask[k0 / 32 + i]) << (3 * i);
-#define AC_PHASE_D(THR_, FS_) \
-  phase_d_unit_pairs<C, QUANT, THR_, FS_, K2, R>((FS_ ? s_filt4 : tb.filt4) + k0 + lane, masks, yv, thr_out + off, q_out + off, rs, gr, eps_s2)
+#define AC_PHASE_D(THR_, FS_)                                                                                            \
+  phase_d_unit_pairs<C, QUANT, THR_, FS_, K2, R, FUSED>((FS_ ? s_filt4 : tb.filt4) + k0 + lane, masks, yv, thr_out + off, \
+                                                        q_out + off, rs, gr, eps_s2, rows_live - r0)
               if (filt_smem) {
                 if (thr) AC_PHASE_D(true, true); else AC_PHASE_D(false, true);
               } else {
@@ -1080,6 +1212,11 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     __syncthreads();
     PA_TRACE(slot_i, 3);
 #endif
+    if constexpr (FUSED) {
+      fence_async_smem();                       // this thread's accesses to T are ordered before the next bulk copy
+      __syncthreads();                          // phase D has read its amplitudes: T may receive the next blocks
+      if (tid == 0 && next_i < tiles) issue_x_load(next_i);
+    }
     tile_i = next_i;
     tpar ^= 1;
     ++slot_i;
@@ -1144,7 +1281,7 @@ cudaError_t launch_mma_tile_nb(const PaDeviceTables& tb, const float* y, const f
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
   kernel<<<grid, kThreads, smem, stream>>>(tb, *tb.jobs_host, y, ton_in, omd, thr_scale, thr_out, q_out, frames, tiles,
-                                           pa_sched_slot(tb), ablate);
+                                           pa_sched_slot(tb), ablate, MdctDeviceTables{}, 0, 0);
   count_launch();
   return cudaGetLastError();
 }
@@ -1246,6 +1383,40 @@ cudaError_t pa_expand_threshold(const PaDeviceTables& tb, const float* bark, flo
     case 4: pa_expand_threshold_kernel<4><<<grid, 256, 0, stream>>>(tb.filt4, bark, eps_s2, thr, rows, tb.n); break;
     default: return cudaErrorInvalidValue;
   }
+  return cudaGetLastError();
+}
+
+// ---- the single-pass encoder: x -> (q, step | bark thresholds) without the amplitudes in global memory ------------
+bool pa_encode_fused_supported(const PaDeviceTables& tb, const MdctDeviceTables& mt, int channels) {
+  return channels == 2 && tb.n == 256 && mt.n == 256 && mt.pre_fwd != nullptr && pa_mma_tile_supported(tb, channels) &&
+         static_cast<size_t>(layout2(tb, true).total) * sizeof(float) <= 113 * 1024;
+}
+
+cudaError_t pa_encode_fused(const PaDeviceTables& tb_in, const MdctDeviceTables& mt, const float* x, float drown,
+                            float thr_scale, float* thr_out, float* bark_out, int32_t* q_out, int64_t batches,
+                            int64_t blocks_n, int channels, cudaStream_t stream) {
+  if (!pa_encode_fused_supported(tb_in, mt, channels)) return cudaErrorNotSupported;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(q_out) | reinterpret_cast<uintptr_t>(thr_out) |
+       reinterpret_cast<uintptr_t>(bark_out)) & 15)
+    return cudaErrorMisalignedAddress;
+  PaDeviceTables tb = tb_in;
+  tb.bark_out = bark_out;
+  constexpr int C = 2, FT = kTI / C;
+  const int64_t frames = blocks_n + 1;
+  const int tiles_per_row = static_cast<int>((frames + FT - 1) / FT);
+  const int64_t tiles = batches * tiles_per_row;
+  const size_t smem = static_cast<size_t>(layout2(tb, true).total) * sizeof(float);
+  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
+  per_sm = per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm);
+  const int64_t cap = static_cast<int64_t>(mma_sm_count()) * per_sm;
+  const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
+  auto kernel = pa_mma_tile_kernel<C, true, 256, 2, true>;
+  cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (err != cudaSuccess) return err;
+  kernel<<<grid, kThreads, smem, stream>>>(tb, *tb.jobs_host, x, nullptr, static_cast<float>(1.0 - static_cast<double>(drown)),
+                                           thr_scale, thr_out, q_out, batches * frames, tiles, pa_sched_slot(tb), 0, mt,
+                                           static_cast<int>(blocks_n), tiles_per_row);
+  count_launch();
   return cudaGetLastError();
 }
 

@@ -137,6 +137,20 @@ int ac_mdct_inverse_dequant_compact_f32(const ac_mdct_plan* plan, const ac_pa_pl
                                         const float* bark_thr, float thr_scale, float* x,
                                         int64_t batches, int64_t blocks, int channels, void* stream);
 
+/* Single-pass encoder: MDCTransformer.transform (mdctransformer.py:61-125) -> tonality ->
+ * global_masking_threshold (psychoacoustic.py:102-148) -> quantiser in ONE kernel,
+ *   x [B, S, C] -> q int32 [B, S/N + 1, N, C], step_out fp32 same shape (may be NULL) and / or
+ *   bark_thr_out [B, S/N + 1, 64, C] (may be NULL; the compact side information above);
+ * the amplitudes stay in shared memory and never reach global memory: 4 bytes read and 4 + (4 | 1) bytes written per
+ * sample instead of 20.  Bit-identical to ac_mdct_forward_f32 + ac_pa_encode_f32 / ac_pa_encode_compact_f32.
+ * Fused for stereo signals with filters_n = 256 (ac_codec_encode_workspace_bytes returns 0: workspace may be NULL);
+ * every other shape runs the two kernels through `workspace`, device memory of that many bytes (the amplitudes). */
+int64_t ac_codec_encode_workspace_bytes(const ac_mdct_plan* mdct, const ac_pa_plan* pa, int64_t batches,
+                                        int64_t samples, int channels);
+int ac_codec_encode_f32(const ac_mdct_plan* mdct, const ac_pa_plan* pa, const float* x, float drown, float thr_scale,
+                        float* step_out, float* bark_thr_out, int32_t* q,
+                        int64_t batches, int64_t samples, int channels, void* workspace, void* stream);
+
 /* PsychoacousticModel.add_noise (psychoacoustic.py:150-167): out = y + thr * N(0, 1/6), counter-based RNG. */
 int ac_pa_add_noise_f32(const float* y, const float* thr, float* out, int64_t n, uint64_t seed, void* stream);
 

@@ -80,3 +80,13 @@ for k in ("AC_PA_ABLATE", "AC_PA_CTAS"):
 print(f"K1: back to back {back_to_back(k1):.2f} us, per launch {per_launch(k1):.2f} us")
 print(f"K2: back to back {back_to_back(k2):.2f} us, per launch {per_launch(k2):.2f} us")
 print(f"chain K1 K3 K2: back to back {back_to_back(chain):.2f} us, with an event after each step {per_launch(chain):.2f} us")
+if c == 2 and n == 256:
+  def kf():
+    _capi.check(lib.ac_codec_encode_f32(mplan, pplan, x.data_ptr(), 0.0, 1.0, step.data_ptr(), None, q.data_ptr(), b, s, c, None, sp))
+  def kfq():
+    _capi.check(lib.ac_codec_encode_f32(mplan, pplan, x.data_ptr(), 0.0, 1.0, None, None, q.data_ptr(), b, s, c, None, sp))
+  print(f"fused encoder (x -> q, step): back to back {back_to_back(kf):.2f} us, per launch {per_launch(kf):.2f} us")
+  print(f"fused encoder (x -> q only): back to back {back_to_back(kfq):.2f} us")
+  def chain2():
+    kf(); k2()
+  print(f"chain fused K2: back to back {back_to_back(chain2):.2f} us, with an event after each step {per_launch(chain2):.2f} us")
