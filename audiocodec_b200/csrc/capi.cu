@@ -850,21 +850,23 @@ int ac_dequantize_f32(const int32_t* q, const float* thr, float* y, int64_t n, v
 }
 
 // --------------------------------------------------------------------------------- host-buffer streaming
-// Device memory is plentiful (180 GB): the whole batch of x and x_hat is staged on the device, so the H2D stream
-// never waits for the kernels and the D2H stream only trails them; amplitudes, steps and integers need one
-// chunk-sized set because the kernels of all chunks run in order on one stream.
+// A ring of kRingSlots chunk-sized device buffers for x and x_hat: the device footprint is a few chunks whatever the
+// size of the host batch (cfg5 streams through one or two GPUs), the H2D stream runs up to kRingSlots chunks ahead of
+// the kernels and the D2H stream trails them.  Amplitudes, steps and integers need one chunk-sized set because the
+// kernels of all chunks run in order on one stream.
 struct ac_codec_pipeline {
+  static constexpr int kRingSlots = 4;
   const ac_mdct_plan* mdct = nullptr;
   const ac_pa_plan* pa = nullptr;
   int64_t chunk_clips = 0, samples = 0;
   int channels = 0, device = 0;
   cudaStream_t h2d = nullptr, run = nullptr, d2h = nullptr;
-  cudaEvent_t entry = nullptr, done = nullptr;
+  cudaEvent_t entry = nullptr, done = nullptr, stats_ready = nullptr;
   float *y = nullptr, *step = nullptr;        // one chunk
   int32_t* q = nullptr;
-  float *x_all = nullptr, *xhat_all = nullptr;   // capacity_clips clips, grown on demand
-  int64_t capacity_clips = 0;
-  std::vector<cudaEvent_t> x_ready, out_ready;   // one pair per chunk of the largest batch seen
+  float *x_ring = nullptr, *xhat_ring = nullptr;   // kRingSlots chunks each
+  // per slot: x has landed (h2d), the forward MDCT has read x (run), x_hat is complete (run), x_hat is on the host (d2h)
+  cudaEvent_t x_ready[kRingSlots] = {}, x_free[kRingSlots] = {}, out_ready[kRingSlots] = {}, out_free[kRingSlots] = {};
   unsigned long long* stats_dev = nullptr;   // [3] coefficients, non-zeros, fixed-point sum of log2(2|q|+1)
 };
 
@@ -873,13 +875,15 @@ int ac_codec_pipeline_destroy(ac_codec_pipeline* p) {
   cudaFree(p->y);
   cudaFree(p->step);
   cudaFree(p->q);
-  cudaFree(p->x_all);
-  cudaFree(p->xhat_all);
+  cudaFree(p->x_ring);
+  cudaFree(p->xhat_ring);
   cudaFree(p->stats_dev);
-  for (cudaEvent_t e : p->x_ready) cudaEventDestroy(e);
-  for (cudaEvent_t e : p->out_ready) cudaEventDestroy(e);
+  for (int i = 0; i < ac_codec_pipeline::kRingSlots; ++i)
+    for (cudaEvent_t e : {p->x_ready[i], p->x_free[i], p->out_ready[i], p->out_free[i]})
+      if (e) cudaEventDestroy(e);
   if (p->entry) cudaEventDestroy(p->entry);
   if (p->done) cudaEventDestroy(p->done);
+  if (p->stats_ready) cudaEventDestroy(p->stats_ready);
   if (p->h2d) cudaStreamDestroy(p->h2d);
   if (p->run) cudaStreamDestroy(p->run);
   if (p->d2h) cudaStreamDestroy(p->d2h);
@@ -906,6 +910,8 @@ int ac_codec_pipeline_create(const ac_mdct_plan* mdct, const ac_pa_plan* pa, int
   p->channels = channels;
   const size_t frames = static_cast<size_t>(samples / n + 1);
   const size_t amp_elems = std::max<size_t>(static_cast<size_t>(chunk_clips) * frames * n * channels, 4);
+  const size_t in_elems = std::max<size_t>(static_cast<size_t>(chunk_clips) * samples * channels, 4);
+  const size_t out_elems = static_cast<size_t>(chunk_clips) * (frames + 1) * n * channels;
   cudaError_t err = cudaGetDevice(&p->device);
   auto ok = [&](cudaError_t e) {
     if (err == cudaSuccess) err = e;
@@ -916,10 +922,19 @@ int ac_codec_pipeline_create(const ac_mdct_plan* mdct, const ac_pa_plan* pa, int
   ok(cudaStreamCreateWithFlags(&p->d2h, cudaStreamNonBlocking));
   ok(cudaEventCreateWithFlags(&p->entry, cudaEventDisableTiming));
   ok(cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming));
+  ok(cudaEventCreateWithFlags(&p->stats_ready, cudaEventDisableTiming));
+  for (int i = 0; i < ac_codec_pipeline::kRingSlots; ++i) {
+    ok(cudaEventCreateWithFlags(&p->x_ready[i], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&p->x_free[i], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&p->out_ready[i], cudaEventDisableTiming));
+    ok(cudaEventCreateWithFlags(&p->out_free[i], cudaEventDisableTiming));
+  }
   ok(cudaMalloc(reinterpret_cast<void**>(&p->stats_dev), 3 * sizeof(unsigned long long)));
   ok(cudaMalloc(reinterpret_cast<void**>(&p->y), amp_elems * sizeof(float)));
   ok(cudaMalloc(reinterpret_cast<void**>(&p->step), amp_elems * sizeof(float)));
   ok(cudaMalloc(reinterpret_cast<void**>(&p->q), amp_elems * sizeof(int32_t)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&p->x_ring), ac_codec_pipeline::kRingSlots * in_elems * sizeof(float)));
+  ok(cudaMalloc(reinterpret_cast<void**>(&p->xhat_ring), ac_codec_pipeline::kRingSlots * out_elems * sizeof(float)));
   if (err != cudaSuccess) {
     ac_codec_pipeline_destroy(p);
     return cuda_fail(err, "creating the streaming pipeline");
@@ -934,25 +949,20 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
   if (batches < 0) return fail(AC_ERR_INVALID, "negative batch");
   if (!(thr_scale > 0.f)) return fail(AC_ERR_INVALID, "thr_scale must be positive");
   if (batches > 0 && (x_host == nullptr || xhat_host == nullptr)) return fail(AC_ERR_INVALID, "null host buffer");
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != p->device)
+    return fail(AC_ERR_INVALID, "pipeline was created on cuda:%d but the current device is cuda:%d", p->device, dev);
+  constexpr int K = ac_codec_pipeline::kRingSlots;
   const int n = p->mdct->tb.n, c = p->channels;
   const int64_t s = p->samples, blocks = s / n, frames = blocks + 1;
   const size_t in_clip = static_cast<size_t>(s) * c, out_clip = static_cast<size_t>(frames + 1) * n * c;
+  const size_t in_slot = std::max<size_t>(static_cast<size_t>(p->chunk_clips) * in_clip, 4);
+  const size_t out_slot = static_cast<size_t>(p->chunk_clips) * out_clip;
   cudaError_t err = cudaSuccess;
   auto ok = [&](cudaError_t e) {
     if (err == cudaSuccess) err = e;
     return err == cudaSuccess;
   };
-  // staging for the whole batch and one event pair per chunk (grown on demand, kept for the next call)
-  if (batches > p->capacity_clips) {
-    cudaFree(p->x_all);
-    cudaFree(p->xhat_all);
-    p->x_all = p->xhat_all = nullptr;
-    p->capacity_clips = 0;
-    ok(cudaMalloc(reinterpret_cast<void**>(&p->x_all), std::max<size_t>(batches * in_clip, 4) * sizeof(float)));
-    ok(cudaMalloc(reinterpret_cast<void**>(&p->xhat_all), batches * out_clip * sizeof(float)));
-    if (err != cudaSuccess) return cuda_fail(err, "allocating the device staging of the batch");
-    p->capacity_clips = batches;
-  }
   // chunk schedule: small chunks at both ends (1, 1, 2, 4, ... clips up to chunk_clips and down again) keep the
   // fill (first H2D + kernels before the first D2H can start) and the drain (last kernels + D2H) of the pipeline
   // short; the middle runs at the full chunk size
@@ -977,44 +987,45 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
     chunk_of.insert(chunk_of.end(), tail.rbegin(), tail.rend());
   }
   const size_t n_chunks = chunk_of.size();
-  while (p->x_ready.size() < n_chunks && err == cudaSuccess) {
-    cudaEvent_t a = nullptr, b = nullptr;
-    ok(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
-    ok(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-    if (err == cudaSuccess) {
-      p->x_ready.push_back(a);
-      p->out_ready.push_back(b);
-    }
-  }
   cudaStream_t caller = static_cast<cudaStream_t>(stream);
   ok(cudaEventRecord(p->entry, caller));
   ok(cudaStreamWaitEvent(p->h2d, p->entry, 0));
   ok(cudaStreamWaitEvent(p->run, p->entry, 0));
   ok(cudaStreamWaitEvent(p->d2h, p->entry, 0));
   if (stats != nullptr) ok(cudaMemsetAsync(p->stats_dev, 0, 3 * sizeof(unsigned long long), p->run));
-  // all the H2D copies first: nothing on that stream depends on the kernels
+  // Per chunk k (slot k mod K), enqueued in this order so that every event is recorded before it is waited for:
+  //   h2d: wait until the forward MDCT of chunk k - K has read the slot's x      -> copy x      -> x_ready
+  //   run: wait for x_ready and until x_hat of chunk k - K has left the slot     -> four kernels -> x_free, out_ready
+  //   d2h: wait for out_ready                                                    -> copy x_hat   -> out_free
+  // The host thread runs ahead of the GPU, so the copy engines see up to K chunks of work queued behind the kernels.
   size_t k = 0;
   for (int64_t i = 0; k < n_chunks && err == cudaSuccess; i += chunk_of[k], ++k) {
     const int64_t cb = chunk_of[k];
+    const int slot = static_cast<int>(k % K);
+    float* xs = p->x_ring + slot * in_slot;
+    float* xh = p->xhat_ring + slot * out_slot;
+    if (k >= K) ok(cudaStreamWaitEvent(p->h2d, p->x_free[slot], 0));
     if (in_clip > 0)
-      ok(cudaMemcpyAsync(p->x_all + i * in_clip, x_host + i * in_clip, cb * in_clip * sizeof(float), cudaMemcpyHostToDevice, p->h2d));
-    ok(cudaEventRecord(p->x_ready[k], p->h2d));
-  }
-  k = 0;
-  for (int64_t i = 0; k < n_chunks && err == cudaSuccess; i += chunk_of[k], ++k) {
-    const int64_t cb = chunk_of[k];
-    float* xh = p->xhat_all + i * out_clip;
-    ok(cudaStreamWaitEvent(p->run, p->x_ready[k], 0));
-    ok(ac::mdct_forward(p->mdct->tb, p->x_all + i * in_clip, p->y, cb, blocks, c, p->run));
+      ok(cudaMemcpyAsync(xs, x_host + i * in_clip, cb * in_clip * sizeof(float), cudaMemcpyHostToDevice, p->h2d));
+    ok(cudaEventRecord(p->x_ready[slot], p->h2d));
+    ok(cudaStreamWaitEvent(p->run, p->x_ready[slot], 0));
+    if (k >= K) ok(cudaStreamWaitEvent(p->run, p->out_free[slot], 0));
+    ok(ac::mdct_forward(p->mdct->tb, xs, p->y, cb, blocks, c, p->run));
+    ok(cudaEventRecord(p->x_free[slot], p->run));
     ok(ac::pa_threshold(p->pa->tb, p->y, nullptr, drown, thr_scale, p->step, p->q, cb * frames, c, p->run));
     if (stats != nullptr) ok(ac::codec_stats(p->q, cb * frames * n * c, p->stats_dev, p->run));
     ok(ac::mdct_inverse(p->mdct->tb, nullptr, p->q, p->step, xh, cb, frames, c, p->run));
-    ok(cudaEventRecord(p->out_ready[k], p->run));
-    ok(cudaStreamWaitEvent(p->d2h, p->out_ready[k], 0));
+    ok(cudaEventRecord(p->out_ready[slot], p->run));
+    ok(cudaStreamWaitEvent(p->d2h, p->out_ready[slot], 0));
     ok(cudaMemcpyAsync(xhat_host + i * out_clip, xh, cb * out_clip * sizeof(float), cudaMemcpyDeviceToHost, p->d2h));
+    ok(cudaEventRecord(p->out_free[slot], p->d2h));
   }
   unsigned long long host_stats[3] = {0, 0, 0};
-  if (stats != nullptr) ok(cudaMemcpyAsync(host_stats, p->stats_dev, sizeof(host_stats), cudaMemcpyDeviceToHost, p->d2h));
+  if (stats != nullptr) {
+    ok(cudaEventRecord(p->stats_ready, p->run));      // also orders the memset before the copy when there are no chunks
+    ok(cudaStreamWaitEvent(p->d2h, p->stats_ready, 0));
+    ok(cudaMemcpyAsync(host_stats, p->stats_dev, sizeof(host_stats), cudaMemcpyDeviceToHost, p->d2h));
+  }
   ok(cudaEventRecord(p->done, p->d2h));
   ok(cudaStreamWaitEvent(caller, p->done, 0));
   ok(cudaEventSynchronize(p->done));          // the result is host memory: hand it back complete

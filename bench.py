@@ -219,11 +219,142 @@ def device_synthetic_audio(torch, b, s, c, sr, first_clip, device):
   return x
 
 
+class Chain:
+  """The device-resident encode + decode chain of one workload on the current device: buffers, the three launches
+  through the C ABI and their algorithmic bytes (compulsory traffic only)."""
+
+  def __init__(self, torch, name, device, first_clip=0, batch=0, x=None):
+    import audiocodec_b200
+    from audiocodec_b200 import _capi
+    self.torch, self.capi, self.lib, self.name, self.device = torch, _capi, _capi.lib(), name, device
+    b, c, sr, s, n = workload_shape(name)
+    if batch:
+      b = batch
+    self.b, self.c, self.sr, self.s, self.n = b, c, sr, s, n
+    self.frames = frames = s // n + 1
+    self.codec = audiocodec_b200.AudioCodec(sr, filters_n=n)
+    self.mplan, self.pplan = self.codec.mdct._plan(device), self.codec.psychoacoustic._plan(device)
+    self.x = x if x is not None else device_synthetic_audio(torch, b, s, c, sr, first_clip=first_clip, device=device)
+    self.y = torch.empty(b, frames, n, c, device=device, dtype=torch.float32)
+    self.q = torch.empty(b, frames, n, c, device=device, dtype=torch.int32)
+    self.step = torch.empty(b, frames, n, c, device=device, dtype=torch.float32)
+    self.xhat = torch.empty(b, (frames + 1) * n, c, device=device, dtype=torch.float32)
+    self.stream = torch.cuda.current_stream(device)
+    sp = self.stream.cuda_stream
+    lib, chk = self.lib, _capi.check
+    self.kernels = [
+      ("mdct_forward", lambda: chk(lib.ac_mdct_forward_f32(self.mplan, self.x.data_ptr(), self.y.data_ptr(), b, s, c, sp))),
+      ("pa_encode", lambda: chk(lib.ac_pa_encode_f32(self.pplan, self.y.data_ptr(), 0.0, 1.0, self.step.data_ptr(),
+                                                      self.q.data_ptr(), b, frames, c, sp))),
+      ("mdct_inverse_dequant", lambda: chk(lib.ac_mdct_inverse_dequant_f32(self.mplan, self.q.data_ptr(), self.step.data_ptr(),
+                                                                            self.xhat.data_ptr(), b, frames, c, sp))),
+    ]
+    rows = b * c
+    self.alg_bytes = {
+      "mdct_forward": 4 * rows * ((frames - 1) * n + frames * n),
+      "pa_encode": 4 * rows * frames * 3 * n,
+      "mdct_inverse_dequant": 4 * rows * (2 * frames * n + (frames + 1) * n),
+    }
+    self.audio_s = b * s / sr
+
+  def step_once(self):
+    for _, fn in self.kernels:
+      fn()
+
+  def time(self, steps, warmup, barrier):
+    """`steps` passes of the chain with a CUDA event after every kernel; returns (total ms, {kernel: mean ms})."""
+    torch = self.torch
+    for _ in range(max(warmup, 3)):
+      self.step_once()
+    barrier()
+    marks = [[torch.cuda.Event(enable_timing=True) for _ in range(len(self.kernels) + 1)] for _ in range(steps)]
+    barrier()
+    for i in range(steps):
+      marks[i][0].record(self.stream)
+      for j, (_, fn) in enumerate(self.kernels):
+        fn()
+        marks[i][j + 1].record(self.stream)
+    barrier()
+    total_ms = marks[0][0].elapsed_time(marks[-1][-1])
+    per_kernel = {name: statistics.fmean(marks[i][j].elapsed_time(marks[i][j + 1]) for i in range(steps))
+                  for j, (name, _) in enumerate(self.kernels)}
+    return total_ms, per_kernel
+
+  def kernel_table(self, per_kernel_ms, peak):
+    out = {}
+    for name, _ in self.kernels:
+      gbs = self.alg_bytes[name] / (per_kernel_ms[name] * 1e-3) / 1e9
+      out[name] = {"ms": per_kernel_ms[name], "alg_bytes": self.alg_bytes[name], "gbs": gbs, "frac": gbs / peak}
+    return out
+
+
+def measured_peak():
+  try:
+    with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+      return float(json.load(f).get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+  except (OSError, ValueError):
+    return 6650.0, "fallback"
+
+
+def other_workloads(torch, device, peak, barrier, skip):
+  """Device-resident chain of the other BASELINE configs on this GPU (5 steps each, after the headline timing)."""
+  out = {}
+  for name in ("cfg1", "cfg3", "cfg4", "cfg5shard"):
+    if name == skip:
+      continue
+    try:
+      chain = Chain(torch, name, device)
+      total_ms, per_kernel = chain.time(5, 3, barrier)
+      ms = total_ms / 5
+      entry = {"workload": describe(name), "ms_per_step": ms, "value": chain.audio_s / (ms * 1e-3), "unit": UNIT,
+               "kernels": {k: {"ms": v["ms"], "frac": v["frac"]} for k, v in chain.kernel_table(per_kernel, peak).items()}}
+      if name == "cfg4":      # BASELINE configs[3]: the psychoacoustic kernel isolated (threshold + quantiser at a fixed scale)
+        entry["pa_encode_only_value"] = chain.audio_s / (per_kernel["pa_encode"] * 1e-3)
+      out[name] = entry
+      del chain
+      torch.cuda.empty_cache()
+    except Exception as e:   # a workload that does not fit is reported, not fatal
+      out[name] = {"error": repr(e)[:200]}
+  return out
+
+
+def cfg5_sweep(torch, dist, device, rank, world, barrier):
+  """BASELINE configs[4] as specified: 8192 stereo clips x 30 s, filters_n = 256, sharded over the ranks (8192 / world
+  clips each, contiguous slices of the batch axis, no collective on the data path), every rank working through its
+  shard in chunks of at most 1024 clips (10.8 GB per tensor) over one set of buffers.  The chunk's clips are generated
+  once per rank and re-used for all of its chunks (the kernels' time does not depend on the data); timed with CUDA
+  events, max over ranks."""
+  total_clips = 8192
+  per_rank = total_clips // world
+  chunk = min(1024, per_rank)
+  n_chunks = per_rank // chunk
+  chain = Chain(torch, "cfg5shard", device, first_clip=rank * per_rank, batch=chunk)
+  for _ in range(2):
+    chain.step_once()
+  barrier()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record(chain.stream)
+  for _ in range(n_chunks):
+    chain.step_once()
+  e1.record(chain.stream)
+  barrier()
+  ms = e0.elapsed_time(e1)
+  from audiocodec_b200 import sharding
+  ms = sharding.max_over_ranks(torch.tensor([ms], device=device, dtype=torch.float64)).item()
+  audio_s = total_clips * chain.s / chain.sr
+  alg = sum(chain.alg_bytes.values()) * n_chunks * world
+  del chain
+  torch.cuda.empty_cache()
+  return {"workload": "cfg5: 8192 clips x 2 ch x 1322752 samples @ 44100 Hz, filters_n=256, %d clips per rank in %d chunk(s) of %d"
+                      % (per_rank, n_chunks, chunk),
+          "n_gpus": world, "ms": ms, "value": audio_s / (ms * 1e-3), "unit": UNIT, "scaling": "strong",
+          "chain_gbs_per_gpu": alg / world / (ms * 1e-3) / 1e9}
+
+
 def run_b200_arm(args):
   import torch
   import torch.distributed as dist
 
-  import audiocodec_b200
   from audiocodec_b200 import _capi
 
   rank = int(os.environ.get("RANK", "0"))
@@ -233,42 +364,17 @@ def run_b200_arm(args):
     raise SystemExit("bench.py: no CUDA device - audiocodec_b200 has no CPU path (use --impl reference for the CPU port)")
   torch.cuda.set_device(local_rank)
   device = torch.device("cuda", local_rank)
+  bind_to_gpu_numa_node(local_rank)
   if world > 1:
     dist.init_process_group("nccl", device_id=device)
 
-  b, c, sr, s, n = workload_shape(args.workload)
-  if args.batch:
-    b = args.batch
-  frames = s // n + 1
   lib = _capi.lib()
-  codec = audiocodec_b200.AudioCodec(sr, filters_n=n)
-  mdct, pa = codec.mdct, codec.psychoacoustic
-  mplan, pplan = mdct._plan(device), pa._plan(device)
-
-  x = device_synthetic_audio(torch, b, s, c, sr, first_clip=rank * b, device=device)
-  y = torch.empty(b, frames, n, c, device=device, dtype=torch.float32)
-  q = torch.empty(b, frames, n, c, device=device, dtype=torch.int32)
-  step_t = torch.empty(b, frames, n, c, device=device, dtype=torch.float32)
-  xhat = torch.empty(b, (frames + 1) * n, c, device=device, dtype=torch.float32)
-  stream = torch.cuda.current_stream(device)
-  sp = stream.cuda_stream
-
-  def k1():
-    _capi.check(lib.ac_mdct_forward_f32(mplan, x.data_ptr(), y.data_ptr(), b, s, c, sp))
-
-  def k3():
-    _capi.check(lib.ac_pa_encode_f32(pplan, y.data_ptr(), 0.0, 1.0, step_t.data_ptr(), q.data_ptr(), b, frames, c, sp))
-
-  def k2():
-    _capi.check(lib.ac_mdct_inverse_dequant_f32(mplan, q.data_ptr(), step_t.data_ptr(), xhat.data_ptr(), b, frames, c, sp))
-
-  kernels = [("mdct_forward", k1), ("pa_encode", k3), ("mdct_inverse_dequant", k2)]
+  chain = Chain(torch, args.workload, device, first_clip=0, batch=args.batch)
+  if rank:      # every rank its own clips of the batch axis
+    chain.x.copy_(device_synthetic_audio(torch, chain.b, chain.s, chain.c, chain.sr, first_clip=rank * chain.b, device=device))
+  b, c, sr, s, n, frames = chain.b, chain.c, chain.sr, chain.s, chain.n, chain.frames
+  codec, x, q, xhat, stream = chain.codec, chain.x, chain.q, chain.xhat, chain.stream
   rows = b * c
-  alg_bytes = {   # compulsory traffic only
-    "mdct_forward": 4 * rows * ((frames - 1) * n + frames * n),
-    "pa_encode": 4 * rows * frames * 3 * n,
-    "mdct_inverse_dequant": 4 * rows * (2 * frames * n + (frames + 1) * n),
-  }
 
   def barrier():
     if world > 1:
@@ -277,41 +383,27 @@ def run_b200_arm(args):
 
   # ---- device-resident timing -----------------------------------------------------------------------
   for _ in range(max(args.warmup, 3)):
-    for _, fn in kernels:
-      fn()
+    chain.step_once()
   barrier()
   sampler = ClockSampler(local_rank if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
                          os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
-  if rank == 0:
-    sampler.start()
-    time.sleep(0.3)
-  marks = [[torch.cuda.Event(enable_timing=True) for _ in range(len(kernels) + 1)] for _ in range(args.steps)]
+  sampler.start()
+  time.sleep(0.3)
   launches0 = lib.ac_kernel_launch_count()
-  barrier()
   t_wall0 = time.perf_counter()
-  for i in range(args.steps):
-    marks[i][0].record(stream)
-    for j, (_, fn) in enumerate(kernels):
-      fn()
-      marks[i][j + 1].record(stream)
-  barrier()
+  total_ms, per_kernel_ms = chain.time(args.steps, 0, barrier)
   t_wall1 = time.perf_counter()
   launches = lib.ac_kernel_launch_count() - launches0
-  total_ms = marks[0][0].elapsed_time(marks[-1][-1])
-  per_kernel_ms = {name: statistics.fmean(marks[i][j].elapsed_time(marks[i][j + 1]) for i in range(args.steps))
-                   for j, (name, _) in enumerate(kernels)}
 
   # keep the GPU under load a little longer if the timed region was too short for a clock sample
-  if rank == 0:
-    t_hold = time.perf_counter()
-    while time.perf_counter() - t_hold < 0.6:
-      for _, fn in kernels:
-        fn()
-      torch.cuda.synchronize(device)
-    t_load_end = time.perf_counter()
+  t_hold = time.perf_counter()
+  while time.perf_counter() - t_hold < 0.6:
+    chain.step_once()
+    torch.cuda.synchronize(device)
+  t_load_end = time.perf_counter()
 
   # ---- end to end through the public API with host buffers ------------------------------------------
-  e2e_ms, e2e_steps, h2d_bytes, d2h_bytes = float("nan"), 0, 0, 0
+  e2e_ms, e2e_steps, h2d_bytes, d2h_bytes, floor_ms = float("nan"), 0, 0, 0, float("nan")
   if not args.no_e2e:
     x_host = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
     x_host.copy_(x)
@@ -330,35 +422,39 @@ def run_b200_arm(args):
     barrier()
     te1 = time.perf_counter()
     e2e_ms = max(e0.elapsed_time(e1), 1e3 * (te1 - te0)) / e2e_steps   # the call returns host data: host-side waits count
-  if rank == 0:
-    sampler.stop()
+    # the floor of that call on this box with `world` ranks copying at once: the same bytes in the same chunks over
+    # the same two copy streams, no kernels (all ranks run it together, max over ranks below)
+    floor_ms = copy_only_floor(torch, x_host, out_host, x, xhat, barrier, e2e_steps)
+  sampler.stop()
 
   # ---- aggregate over ranks: max time, gathered bitstream statistics ---------------------------------
   from audiocodec_b200 import sharding
-  times = sharding.max_over_ranks(torch.tensor([total_ms, e2e_ms], device=device, dtype=torch.float64))
+  clocks = sampler.summary(t_wall0 - 0.05, t_load_end)
+  times = sharding.max_over_ranks(torch.tensor([total_ms, e2e_ms, floor_ms], device=device, dtype=torch.float64))
+  clock_min = -sharding.max_over_ranks(torch.tensor([-(clocks["sm_mhz"] or 0.0)], device=device, dtype=torch.float64)).item()
   # the one collective of the job: bitstream sizes and statistics of every shard
   stats = sharding.gather_stats(codec.stats(q).to(torch.float64)).sum(0)
-  total_ms, e2e_ms = times.tolist()
+  total_ms, e2e_ms, floor_ms = times.tolist()
   ok = bool(torch.isfinite(xhat).all().item())
   err = (xhat[:, n:-n] - x).float().pow(2).mean().sqrt().item()
+  peak, peak_src = measured_peak()
+
+  extra = {}
+  if not args.no_other_workloads:
+    del chain.y, chain.step
+    if world == 1:
+      extra["other_workloads"] = other_workloads(torch, device, peak, barrier, skip=args.workload)
+    try:
+      extra["cfg5_sweep"] = cfg5_sweep(torch, dist, device, rank, world, barrier)
+    except Exception as e:
+      extra["cfg5_sweep"] = {"error": repr(e)[:200]}
 
   if rank == 0:
     audio_s_per_step = world * b * s / sr
     ms_per_step = total_ms / args.steps
     value = audio_s_per_step / (ms_per_step * 1e-3)
-    peaks = {}
-    peak_src = "fallback"
-    try:
-      with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-        peaks = json.load(f)
-      peak_src = "measured"
-    except OSError:
-      pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    per_kernel = {}
-    for name, _ in kernels:
-      gbs = alg_bytes[name] / (per_kernel_ms[name] * 1e-3) / 1e9
-      per_kernel[name] = {"ms": per_kernel_ms[name], "alg_bytes": alg_bytes[name], "gbs": gbs, "frac": gbs / peak}
+    per_kernel = chain.kernel_table(per_kernel_ms, peak)
+    alg_bytes = chain.alg_bytes
     dominant = max(per_kernel, key=lambda k: per_kernel[k]["ms"])
     traffic = None
     try:
@@ -366,6 +462,7 @@ def run_b200_arm(args):
         traffic = json.load(f).get(args.workload, {}).get(dominant)
     except (OSError, ValueError):
       pass
+    clocks["sm_mhz_min_over_ranks"] = clock_min
     line = {
       "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
       "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -373,21 +470,23 @@ def run_b200_arm(args):
       "config": bench_config(args.workload, b, c, s, n),
       "e2e": {"value": audio_s_per_step / (e2e_ms * 1e-3) if e2e_steps else None, "unit": UNIT,
               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_ms if e2e_steps else None,
-              "steps": e2e_steps,
+              "steps": e2e_steps, "copy_floor_ms": floor_ms if e2e_steps else None,
+              "copy_floor": "the same bytes over the same two copy streams in the same chunks, no kernels, all ranks at once, "
+                            "max over ranks",
               "api": "AudioCodec.roundtrip_host(pinned x) -> pinned x_hat"},
       "gpu_launches": int(launches),
       "roofline": {"bound": "hbm", "kernel": dominant, "achieved": per_kernel[dominant]["gbs"], "peak": peak,
-                   "peak_source": peak_src + " (MEASURED_PEAKS.json hbm_gbs)" if peak_src == "measured" else "fallback",
-                   "unit": "GB/s", "frac": per_kernel[dominant]["frac"], "traffic": traffic,
+                   "peak_source": peak_src, "unit": "GB/s", "frac": per_kernel[dominant]["frac"], "traffic": traffic,
                    "traffic_source": "profiles/dram_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one "
                                      "ncu --set full capture of this kernel on this workload; not measured in this run)",
                    "chain_gbs": sum(alg_bytes.values()) / (ms_per_step * 1e-3) / 1e9,
                    "chain_frac": sum(alg_bytes.values()) / (ms_per_step * 1e-3) / 1e9 / peak},
       "kernels": per_kernel,
-      "clocks": sampler.summary(t_wall0 - 0.05, t_load_end),
+      "clocks": clocks,
       "stats": {"coefficients": stats[0].item(), "nonzero": stats[1].item(), "bits_estimate": stats[2].item(),
                 "roundtrip_rms_error": err, "finite": ok},
     }
+    line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
       v, info = cpu_port_throughput(args.workload, budget_s=20.0, steps=2, warmup=1)
       line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
@@ -395,6 +494,53 @@ def run_b200_arm(args):
   if world > 1:
     dist.destroy_process_group()
   return 0
+
+
+def copy_only_floor(torch, x_host, out_host, x_dev, out_dev, barrier, steps):
+  """Pinned host -> device and device -> host copies of one step's bytes, in ~30 MB pieces on two streams at once."""
+  h2d, d2h = torch.cuda.Stream(), torch.cuda.Stream()
+  xh, oh = x_host.view(-1), out_host.view(-1)
+  xd, od = x_dev.view(-1), out_dev.view(-1)
+  piece = (30 << 20) // 4
+
+  def once():
+    with torch.cuda.stream(h2d):
+      for i in range(0, xh.numel(), piece):
+        xd[i:i + piece].copy_(xh[i:i + piece], non_blocking=True)
+    with torch.cuda.stream(d2h):
+      for i in range(0, oh.numel(), piece):
+        oh[i:i + piece].copy_(od[i:i + piece], non_blocking=True)
+
+  once()
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    once()
+  h2d.synchronize()
+  d2h.synchronize()
+  return 1e3 * (time.perf_counter() - t0) / steps
+
+
+def bind_to_gpu_numa_node(local_rank):
+  """Keeps this rank's host threads (and so its pinned allocations, first touch) on the CPUs nearest to its GPU: with
+  eight ranks streaming at once the copies otherwise cross the socket interconnect.  Silently does nothing where the
+  topology cannot be read."""
+  try:
+    import pynvml
+    pynvml.nvmlInit()
+    idx = local_rank
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+      idx = int(vis.split(",")[local_rank])
+    h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+    words = (os.cpu_count() + 63) // 64
+    mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+    cpus = {64 * w + bit for w, m in enumerate(mask) for bit in range(64) if (m >> bit) & 1}
+    cpus &= os.sched_getaffinity(0)
+    if cpus:
+      os.sched_setaffinity(0, cpus)
+  except Exception:
+    pass
 
 
 def main():
@@ -407,6 +553,7 @@ def main():
   ap.add_argument("--batch", type=int, default=0, help="override the per-GPU clip count (debug)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (exploration runs of the big configs)")
+  ap.add_argument("--no-other-workloads", action="store_true", help="skip the other BASELINE configs and the cfg5 sweep")
   args = ap.parse_args()
   if args.impl == "reference":
     return run_reference_arm(args)

@@ -183,8 +183,9 @@ int ac_dequantize_f64(const int32_t* q, const double* thr, double* y, int64_t n,
 
 /* ------------------------------------------------------------------------- host-buffer streaming */
 /* encode + decode of clips that live in HOST memory (the call a file / network front end makes; no reference
- * symbol - the reference leaves data movement to TensorFlow).  The pipeline owns three streams, device staging
- * for the whole batch of x and x_hat (grown on demand) and one chunk of amplitudes / steps / integers;
+ * symbol - the reference leaves data movement to TensorFlow).  The pipeline owns three streams, a ring of four
+ * chunk-sized device buffers for x and for x_hat and one chunk of amplitudes / steps / integers - its device
+ * footprint does not depend on the size of the host batch (cfg5's 87 GB stream through one GPU);
  * x_host [B, S, C] flows in chunks of `chunk_clips` clips through
  * H2D -> ac_mdct_forward -> ac_pa_encode -> ac_mdct_inverse_dequant -> D2H into xhat_host [B, S + 2N, C] with
  * both PCIe directions and the kernels overlapped.  Pinned host memory gives asynchronous copies (pageable

@@ -386,3 +386,33 @@ def test_bit_estimate_and_rate_loop():
     assert torch.equal(qr, pa.quantize(y, step))
     assert last is None or scale > last          # fewer bits need a coarser step
     last = scale
+
+
+def test_host_streaming_ring_is_bounded_and_reused():
+  """The pipeline stages x / x_hat in a ring of four chunk buffers: many more chunks than slots give the same bits as
+  the device path, and the device footprint does not grow with the host batch (capacity for config 5)."""
+  sr, n, c = 44100, 256, 2
+  codec = audiocodec_b200.AudioCodec(sr, filters_n=n)
+  x = oracle.synthetic_audio(37, 256 * 20, c, sr)
+  q, step = codec.encode(torch.from_numpy(x).cuda())
+  ref = codec.decode(q, step).cpu()
+  xh = torch.from_numpy(x).pin_memory()
+  for chunk in (1, 2):                                  # 37 / 22 chunks through 4 slots
+    assert torch.equal(codec.roundtrip_host(xh, chunk_clips=chunk), ref)
+    assert torch.equal(codec.roundtrip_host(xh, chunk_clips=chunk), ref)      # the ring's events are re-armed
+  del q, step, ref
+  # 192 clips x 30 s (2 GB each way on the host) through 2-clip chunks: the library's device memory stays at a few chunks
+  s = (sr * 30 // n) * n
+  big = torch.empty(192, s, c, dtype=torch.float32).uniform_(-0.5, 0.5)
+  torch.cuda.synchronize()
+  torch.cuda.empty_cache()
+  free0, _ = torch.cuda.mem_get_info()
+  out = codec.roundtrip_host(big, chunk_clips=2)
+  free1, _ = torch.cuda.mem_get_info()
+  clip_bytes = 4 * s * c
+  assert free0 - free1 < 4 * 2 * clip_bytes * 2 + 3 * 2 * clip_bytes + (256 << 20)    # ring (x, x_hat) + Y, q, step + slack
+  assert free0 - free1 < big.numel() * 4 // 4                                         # far below the batch itself
+  probe = [0, 95, 191]
+  dev = torch.stack([big[i] for i in probe]).cuda()
+  qd, sd = codec.encode(dev)
+  assert torch.equal(out[probe], codec.decode(qd, sd).cpu())
