@@ -11,6 +11,7 @@ import os
 from . import build as _build
 
 AC_OK, AC_ERR_INVALID, AC_ERR_CUDA, AC_ERR_UNSUPPORTED, AC_ERR_ALLOC = 0, -1, -2, -3, -4
+DTYPE_F32, DTYPE_BF16 = 0, 1
 WINDOW_ONES, WINDOW_SINE, WINDOW_VORBIS = 0, 1, 2
 
 _c_int64 = ctypes.c_int64
@@ -29,6 +30,7 @@ SIGNATURES = {
   "ac_pa_mma_jobs_host": (ctypes.c_int, [ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_double, _c_void_p,
                                          _c_void_p, _c_void_p, _c_void_p, _c_void_p]),
   "ac_mdct_plan_create": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_c_void_p)]),
+  "ac_mdct_plan_create_ex": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(_c_void_p)]),
   "ac_mdct_plan_destroy": (ctypes.c_int, [_c_void_p]),
   "ac_mdct_forward_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
   "ac_mdct_inverse_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
@@ -38,6 +40,8 @@ SIGNATURES = {
                                                          _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
   "ac_pa_plan_create": (ctypes.c_int, [ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                        ctypes.POINTER(_c_void_p)]),
+  "ac_pa_plan_create_ex": (ctypes.c_int, [ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int,
+                                          ctypes.POINTER(_c_void_p)]),
   "ac_pa_plan_destroy": (ctypes.c_int, [_c_void_p]),
   "ac_pa_tonality_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
   "ac_pa_threshold_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, ctypes.c_float, _c_void_p, _c_int64,
@@ -62,6 +66,14 @@ SIGNATURES = {
                                          _c_int64, ctypes.c_int, _c_void_p]),
   "ac_quantize_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
   "ac_dequantize_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
+  "ac_bf16_workspace_bytes": (_c_int64, [_c_int64, _c_int64]),
+  "ac_mdct_forward_bf16": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p, _c_void_p]),
+  "ac_mdct_inverse_bf16": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p, _c_void_p]),
+  "ac_pa_tonality_bf16": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p, _c_void_p]),
+  "ac_pa_threshold_bf16": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, ctypes.c_float, _c_void_p, _c_int64, _c_int64,
+                                          ctypes.c_int, _c_void_p, _c_void_p]),
+  "ac_pa_amplitude_to_db_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, ctypes.c_int, _c_void_p]),
+  "ac_pa_amplitude_to_db_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, ctypes.c_int, _c_void_p]),
   "ac_codec_pipeline_create": (ctypes.c_int, [_c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int,
                                               ctypes.POINTER(_c_void_p)]),
   "ac_codec_pipeline_destroy": (ctypes.c_int, [_c_void_p]),

@@ -13,15 +13,15 @@ import torch
 
 
 def normalise_compute_dtype(dtype, who):
-  """Accepts tf / torch / numpy dtypes or strings; float32 (the tuned path) and float64 (functional kernels) are built."""
+  """Accepts tf / torch / numpy dtypes or strings: float32 (the tuned path), float64 and bfloat16 (functional paths)."""
   name = getattr(dtype, "name", None) or str(dtype)
   name = name.replace("torch.", "").replace("<dtype: '", "").replace("'>", "")
   if name in ("float32", "float", "f32") or dtype is np.float32:
     return "float32"
   if name in ("float64", "double", "f64") or dtype is np.float64:
     return "float64"
-  if name == "bfloat16":
-    raise NotImplementedError(f"{who}: compute_dtype bfloat16 is accepted by the reference but no bfloat16 kernels are built")
+  if name in ("bfloat16", "bf16"):
+    return "bfloat16"
   raise TypeError(f"compute_dtype of {who} should be float64, float32 or bfloat16 (got {dtype!r})")
 
 
@@ -63,7 +63,13 @@ adopt.copies = 0
 
 
 def torch_dtype(name):
-  return torch.float64 if name == "float64" else torch.float32
+  return {"float64": torch.float64, "bfloat16": torch.bfloat16}.get(name, torch.float32)
+
+
+def bf16_workspace(lib, in_elems, out_elems, device):
+  """float32 scratch of the bfloat16 entry points (the kernels run in float32 on copies of the bfloat16 tensors)."""
+  need = lib.ac_bf16_workspace_bytes(int(in_elems), int(out_elems))
+  return torch.empty(max(need // 4, 4), dtype=torch.float32, device=device)
 
 
 def stream_ptr(device):

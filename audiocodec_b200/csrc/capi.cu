@@ -75,6 +75,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct ac_mdct_plan {
   int device = 0;
+  int compute_dtype = 0;     // ac_compute_dtype
   ac::MdctDeviceTables tb;
   ac::MdctDeviceTables64 tb64;
   std::vector<void*> owned;
@@ -82,6 +83,7 @@ struct ac_mdct_plan {
 
 struct ac_pa_plan {
   int device = 0;
+  int compute_dtype = 0;     // ac_compute_dtype
   ac::PaDeviceTables tb;
   ac::PaDeviceTables64 tb64;
   ac::PaJobParams jobs;
@@ -98,6 +100,19 @@ void free_all(std::vector<void*>& owned) {
 
 int check_window(int window_type) {
   return (window_type == AC_WINDOW_ONES || window_type == AC_WINDOW_SINE || window_type == AC_WINDOW_VORBIS) ? 0 : -1;
+}
+
+// nearest-even rounding of a double to a bfloat16 value (through float32, as tf.cast(float64 -> bfloat16) does)
+double bf16_round(double v) {
+  const float f = static_cast<float>(v);
+  uint32_t u;
+  std::memcpy(&u, &f, sizeof(u));
+  if ((u & 0x7f800000u) == 0x7f800000u) return f;      // inf / nan
+  u += 0x7fffu + ((u >> 16) & 1u);
+  u &= 0xffff0000u;
+  float r;
+  std::memcpy(&r, &u, sizeof(r));
+  return r;
 }
 
 // validates a DLPack tensor and returns its data pointer (incl. byte_offset)
@@ -303,8 +318,14 @@ int ac_pa_mma_jobs_host(double sample_rate, int filter_bands_n, int bark_bands_n
 
 // ------------------------------------------------------------------------------------------------ MDCT
 int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_mdct_plan** out) {
+  return ac_mdct_plan_create_ex(filters_n, window_type, precompute_f32, AC_DTYPE_F32, out);
+}
+
+int ac_mdct_plan_create_ex(int filters_n, int window_type, int precompute_f32, int compute_dtype, ac_mdct_plan** out) {
   if (out == nullptr) return fail(AC_ERR_INVALID, "out is null");
   *out = nullptr;
+  if (compute_dtype != AC_DTYPE_F32 && compute_dtype != AC_DTYPE_BF16)
+    return fail(AC_ERR_INVALID, "compute_dtype must be AC_DTYPE_F32 or AC_DTYPE_BF16 (float64 runs on any plan)");
   if (filters_n < 2 || (filters_n % 2) != 0)
     return fail(AC_ERR_INVALID, "number of filters used in mdct transformation needs to be even (got %d)", filters_n);
   if (check_window(window_type) != 0) return fail(AC_ERR_INVALID, "unknown window type %d", window_type);
@@ -319,9 +340,19 @@ int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_m
     return cuda_fail(err, "cudaGetDevice (no CUDA device? this library has no CPU path)");
   }
   const int n = filters_n, h = n / 2;
-  const ac::MdctTables t = ac::build_mdct_tables(n, window_type, precompute_f32 != 0);
+  ac::MdctTables t = ac::build_mdct_tables(n, window_type, precompute_f32 != 0);
   const double pi = 3.14159265358979323846;
-  const double scale_fwd = 1.0 / (n * std::sqrt(2.0)), scale_inv = 2.0 * std::sqrt(2.0);
+  double scale_fwd = 1.0 / (n * std::sqrt(2.0)), scale_inv = 2.0 * std::sqrt(2.0);
+  plan->compute_dtype = compute_dtype;
+  if (compute_dtype == AC_DTYPE_BF16) {
+    // compute_dtype=tf.bfloat16: H and H_inv are cast to bfloat16 (mdctransformer.py:58-59), and so are the constants
+    // sqrt(2) (:347) and 1 / sqrt(4N), sqrt(4N) (:125, :145); the DCT itself runs in float32 (:326-344)
+    for (double& v : t.fold) v = bf16_round(v);
+    for (double& v : t.unfold) v = bf16_round(v);
+    const double r2 = bf16_round(std::sqrt(2.0)) / std::sqrt(2.0);
+    scale_fwd *= r2 * bf16_round(1.0 / std::sqrt(4.0 * n)) * std::sqrt(4.0 * n);
+    scale_inv *= r2 * bf16_round(std::sqrt(4.0 * n)) / std::sqrt(4.0 * n);
+  }
   std::vector<float4> fold(h), unfold(h);
   std::vector<float2> tw(h), twf(h), twi(h), roots(h);
   for (int p = 0; p < h; ++p) {
@@ -518,8 +549,20 @@ int ac_mdct_inverse_dequant_compact_f32(const ac_mdct_plan* plan, const ac_pa_pl
 
 // ------------------------------------------------------------------------------------- psychoacoustics
 int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha, ac_pa_plan** out) {
+  return ac_pa_plan_create_ex(sample_rate, filter_bands_n, bark_bands_n, alpha, AC_DTYPE_F32, out);
+}
+
+int ac_pa_plan_create_ex(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha_in, int compute_dtype,
+                         ac_pa_plan** out) {
   if (out == nullptr) return fail(AC_ERR_INVALID, "out is null");
   *out = nullptr;
+  if (compute_dtype != AC_DTYPE_F32 && compute_dtype != AC_DTYPE_BF16)
+    return fail(AC_ERR_INVALID, "compute_dtype must be AC_DTYPE_F32 or AC_DTYPE_BF16 (float64 runs on any plan)");
+  const bool bf16 = compute_dtype == AC_DTYPE_BF16;
+  // compute_dtype=tf.bfloat16: python scalars take the tensor's dtype, so alpha and 1 / alpha enter tf.pow as bfloat16
+  // values (psychoacoustic.py:197, 206, 208) - and 1 / alpha is rounded on its own, it is not the inverse of the rounded alpha
+  const double alpha = bf16 ? bf16_round(alpha_in) : alpha_in;
+  const double inv_alpha = bf16 ? bf16_round(1. / alpha_in) : 1. / alpha_in;
   if (!(sample_rate > 0) || filter_bands_n < 1 || bark_bands_n < 1 || !(alpha > 0))
     return fail(AC_ERR_INVALID, "invalid psychoacoustic parameters (sample_rate %g, filter_bands_n %d, bark_bands_n %d, alpha %g)",
                 sample_rate, filter_bands_n, bark_bands_n, alpha);
@@ -532,15 +575,26 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
     delete plan;
     return cuda_fail(err, "cudaGetDevice (no CUDA device? this library has no CPU path)");
   }
-  plan->host = ac::build_pa_tables(sample_rate, filter_bands_n, bark_bands_n, alpha);
+  plan->host = ac::build_pa_tables(sample_rate, filter_bands_n, bark_bands_n, alpha_in);
+  plan->compute_dtype = compute_dtype;
+  if (bf16) {     // W, W_inv, the quiet threshold and the spreading matrix are cast to the compute dtype (:65-69),
+    ac::PaTables& h = plan->host;   // tf.linspace runs in it (:187-189)
+    for (double& v : h.w) v = bf16_round(v);
+    for (double& v : h.w_inv) v = bf16_round(v);
+    for (double& v : h.quiet) v = bf16_round(v);
+    for (double& v : h.spread_fn) v = bf16_round(v);
+    for (float& v : h.lin) v = static_cast<float>(bf16_round(v));
+    for (float& v : h.band_w) v = static_cast<float>(bf16_round(v));
+    for (float& v : h.filt_w) v = static_cast<float>(bf16_round(v));
+  }
   const ac::PaTables& t = plan->host;
   ac::PaDeviceTables& d = plan->tb;
   d.n = t.n;
   d.nb = t.nb;
   d.alpha = static_cast<float>(alpha);
   d.neg_alpha = static_cast<float>(-alpha);
-  d.inv_alpha = static_cast<float>(1. / alpha);
-  d.eps = 1e-14f;
+  d.inv_alpha = static_cast<float>(inv_alpha);
+  d.eps = bf16 ? static_cast<float>(bf16_round(1e-14)) : 1e-14f;
   d.max_band_cnt = t.max_band_cnt;
   d.max_filt_cnt = t.max_filt_cnt;
   d.gain_log2 = static_cast<float>(-alpha * std::log2(10.0) / 10.0);
@@ -611,9 +665,10 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
     return tab;
   };
   const std::vector<float2> pow_alpha = pow_table(d.alpha), pow_inv_alpha = pow_table(d.inv_alpha);
-  d.offset_log2 = static_cast<float>(-std::log2(10.0) / 10.0);
+  // (acc 10^(-alpha offset / 10))^(1 / alpha): the offset's factor is alpha (1 / alpha) = 1, except with both rounded to bfloat16
+  d.offset_log2 = static_cast<float>(-std::log2(10.0) / 10.0 * (bf16 ? alpha * inv_alpha : 1.0));
   d.pow_c1 = static_cast<float>(alpha - 0.5);
-  d.pow_c2 = static_cast<float>(1. / alpha - 2.);
+  d.pow_c2 = static_cast<float>(inv_alpha - 2.);
   // |c| lg2(x) keeps ~2^-24 / |c| of headroom against fp32 rounding of lg2: split powers for alpha in [0.45, 0.65]
   d.pow_split = (alpha >= 0.45 && alpha <= 0.65 && std::getenv("AC_PA_POW_TABLE") == nullptr) ? 1 : 0;
   {
@@ -675,8 +730,8 @@ int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, 
     ac::PaDeviceTables64& e = plan->tb64;
     e.n = t.n;
     e.nb = t.nb;
-    e.alpha = alpha;
-    e.inv_alpha = 1. / alpha;
+    e.alpha = alpha_in;
+    e.inv_alpha = 1. / alpha_in;
     e.eps = 1e-14;
     e.band_k0 = d.band_k0;
     e.band_cnt = d.band_cnt;
@@ -1100,6 +1155,121 @@ int ac_dequantize_f64(const int32_t* q, const double* thr, double* y, int64_t n,
   if (n > 0 && (y == nullptr || thr == nullptr || q == nullptr)) return fail(AC_ERR_INVALID, "null tensor");
   cudaError_t err = ac::dequantize_f64(q, thr, y, n, static_cast<cudaStream_t>(stream));
   return err == cudaSuccess ? AC_OK : cuda_fail(err, "dequantize_f64 launch");
+}
+
+// ------------------------------------------------------------------------------- bfloat16 compute dtype
+// Tensors are bfloat16 at the boundary, the plan's tables and constants are bfloat16 values (ac_*_plan_create_ex with
+// AC_DTYPE_BF16), the kernels run in float32 on float32 copies held in the caller's workspace: the reference's rule for
+// the DCT (mdctransformer.py:326-344) applied to the whole path.  workspace: ac_bf16_workspace_bytes(in, out) bytes.
+static inline int64_t pad4(int64_t n) { return (n + 3) & ~static_cast<int64_t>(3); }
+
+int64_t ac_bf16_workspace_bytes(int64_t in_elems, int64_t out_elems) {
+  if (in_elems < 0 || out_elems < 0) return -1;
+  return 4 * (pad4(in_elems) + pad4(out_elems));
+}
+
+#define AC_REQUIRE_BF16(plan)                                                                                       \
+  if ((plan)->compute_dtype != AC_DTYPE_BF16)                                                                       \
+    return fail(AC_ERR_INVALID, "the plan holds float32 tables: create it with ac_*_plan_create_ex(..., AC_DTYPE_BF16)")
+
+int ac_mdct_forward_bf16(const ac_mdct_plan* plan, const void* x, void* y, int64_t batches, int64_t samples, int channels,
+                         void* workspace, void* stream) {
+  if (int rc = check_common(plan, batches, samples, channels)) return rc;
+  AC_REQUIRE_BF16(plan);
+  const int n = plan->tb.n;
+  if (samples % n != 0)
+    return fail(AC_ERR_INVALID, "samples_n (%lld) must be a multiple of filters_n (%d)", (long long)samples, n);
+  const int64_t blocks = samples / n, in = batches * samples * channels, out = batches * (blocks + 1) * n * channels;
+  if (blocks + 1 > 2147483647LL / 2) return fail(AC_ERR_INVALID, "too many blocks per batch row");
+  if (batches == 0) return AC_OK;
+  if ((x == nullptr && samples > 0) || y == nullptr || workspace == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  if (!aligned16(workspace)) return fail(AC_ERR_INVALID, "workspace must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* xf = static_cast<float*>(workspace);
+  float* yf = xf + pad4(in);
+  cudaError_t err = ac::bf16_to_f32(x, xf, in, st);
+  if (err == cudaSuccess) err = ac::mdct_forward(plan->tb, xf, yf, batches, blocks, channels, st);
+  if (err == cudaSuccess) err = ac::f32_to_bf16(yf, y, out, st);
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "mdct_forward (bfloat16) launch");
+}
+
+int ac_mdct_inverse_bf16(const ac_mdct_plan* plan, const void* y, void* x, int64_t batches, int64_t blocks, int channels,
+                         void* workspace, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  AC_REQUIRE_BF16(plan);
+  const int n = plan->tb.n;
+  const int64_t in = batches * blocks * n * channels, out = batches * (blocks + 1) * n * channels;
+  if (blocks + 1 > 2147483647LL / 2) return fail(AC_ERR_INVALID, "too many blocks per batch row");
+  if (batches == 0) return AC_OK;
+  if ((y == nullptr && blocks > 0) || x == nullptr || workspace == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  if (!aligned16(workspace)) return fail(AC_ERR_INVALID, "workspace must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* yf = static_cast<float*>(workspace);
+  float* xf = yf + pad4(in);
+  cudaError_t err = ac::bf16_to_f32(y, yf, in, st);
+  if (err == cudaSuccess) err = ac::mdct_inverse(plan->tb, yf, nullptr, nullptr, xf, batches, blocks, channels, st);
+  if (err == cudaSuccess) err = ac::f32_to_bf16(xf, x, out, st);
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "mdct_inverse (bfloat16) launch");
+}
+
+int ac_pa_tonality_bf16(const ac_pa_plan* plan, const void* y, void* ton, int64_t batches, int64_t blocks, int channels,
+                        void* workspace, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  AC_REQUIRE_BF16(plan);
+  const int64_t rows = batches * blocks, in = rows * plan->tb.n * channels, out = rows * channels;
+  if (rows == 0) return AC_OK;
+  if (y == nullptr || ton == nullptr || workspace == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  if (!aligned16(workspace)) return fail(AC_ERR_INVALID, "workspace must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* yf = static_cast<float*>(workspace);
+  float* tf = yf + pad4(in);
+  cudaError_t err = ac::bf16_to_f32(y, yf, in, st);
+  if (err == cudaSuccess) err = ac::pa_tonality(plan->tb, yf, tf, rows, channels, st);
+  if (err == cudaSuccess) err = ac::f32_to_bf16(tf, ton, out, st);
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_tonality (bfloat16) launch");
+}
+
+int ac_pa_threshold_bf16(const ac_pa_plan* plan, const void* y, const void* ton, float drown, void* thr, int64_t batches,
+                         int64_t blocks, int channels, void* workspace, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  AC_REQUIRE_BF16(plan);
+  const int64_t rows = batches * blocks, amp = rows * plan->tb.n * channels, tn = ton != nullptr ? rows * channels : 0;
+  if (rows == 0) return AC_OK;
+  if (y == nullptr || thr == nullptr || workspace == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  if (!aligned16(workspace)) return fail(AC_ERR_INVALID, "workspace must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // workspace: [amplitudes | tonality] as the inputs, [threshold] as the output:
+  // ac_bf16_workspace_bytes(amplitudes + 4 * ceil(rows * channels / 4), amplitudes)
+  float* yf = static_cast<float*>(workspace);
+  float* tf = yf + pad4(amp);
+  float* hf = tf + pad4(tn);
+  cudaError_t err = ac::bf16_to_f32(y, yf, amp, st);
+  if (err == cudaSuccess && ton != nullptr) err = ac::bf16_to_f32(ton, tf, tn, st);
+  if (err == cudaSuccess)
+    err = ac::pa_threshold(plan->tb, yf, ton != nullptr ? tf : nullptr, drown, 1.0f, hf, nullptr, rows, channels, st);
+  if (err == cudaSuccess) err = ac::f32_to_bf16(hf, thr, amp, st);
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_threshold (bfloat16) launch");
+}
+
+// ----------------------------------------------------------------------------------------- dB utilities
+int ac_pa_amplitude_to_db_f32(const ac_pa_plan* plan, const float* a, float* out, int64_t n, int normalised, void* stream) {
+  if (plan == nullptr) return fail(AC_ERR_INVALID, "plan is null");
+  if (n < 0) return fail(AC_ERR_INVALID, "negative size");
+  if (n == 0) return AC_OK;
+  if (a == nullptr || out == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::amplitude_to_db_f32(a, out, n, plan->tb.eps, 120.f, plan->host.db_min, normalised != 0,
+                                            static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "amplitude_to_dB launch");
+}
+
+int ac_pa_amplitude_to_db_f64(const ac_pa_plan* plan, const double* a, double* out, int64_t n, int normalised, void* stream) {
+  if (plan == nullptr) return fail(AC_ERR_INVALID, "plan is null");
+  if (n < 0) return fail(AC_ERR_INVALID, "negative size");
+  if (n == 0) return AC_OK;
+  if (a == nullptr || out == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::amplitude_to_db_f64(a, out, n, 1e-14, 120., 10. * std::log(1e-14) / std::log(10.) + 120., normalised != 0,
+                                            static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "amplitude_to_dB launch");
 }
 
 // ---------------------------------------------------------------------------------------------- DLPack

@@ -130,6 +130,14 @@ cudaError_t pa_encode_fused(const PaDeviceTables& tb, const MdctDeviceTables& mt
                             float thr_scale, float* thr_out, float* bark_out, int32_t* q_out, int64_t batches,
                             int64_t blocks_n, int channels, cudaStream_t stream);
 
+// elementwise_kernels.cu: bfloat16 <-> float32 (round to nearest even) and the dB utilities (psychoacoustic.py:71-100)
+cudaError_t bf16_to_f32(const void* in, float* out, int64_t n, cudaStream_t stream);
+cudaError_t f32_to_bf16(const float* in, void* out, int64_t n, cudaStream_t stream);
+cudaError_t amplitude_to_db_f32(const float* a, float* out, int64_t n, float eps, float db_max, float db_min, bool norm,
+                                cudaStream_t stream);
+cudaError_t amplitude_to_db_f64(const double* a, double* out, int64_t n, double eps, double db_max, double db_min, bool norm,
+                                cudaStream_t stream);
+
 // float64 compute dtype (f64_kernels.cu): the same tables in double, sparse forms shared with the fp32 plan
 struct MdctDeviceTables64 {
   int n = 0;

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._tensors import adopt, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr, torch_dtype
+from ._tensors import adopt, bf16_workspace, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr, torch_dtype
 
 
 class MDCTransformer:
@@ -21,7 +21,9 @@ class MDCTransformer:
     :param filters_n:        number of filter bands (needs to be even; AssertionError otherwise, :26)
     :param window_type:      'sine', 'vorbis' (default); any other string selects the rectangular window (:199-211)
     :param compute_dtype:    dtype of inputs and outputs (tf / torch / numpy dtype or string): float32 (the tuned
-                             tile kernels) or float64 (functional kernels); bfloat16 raises NotImplementedError
+                             tile kernels), float64 (functional kernels) or bfloat16 (H / H_inv and the scale constants
+                             cast to bfloat16 as in the reference, float32 arithmetic in between - the reference's own
+                             rule around the DCT, :326-344 - one rounding to bfloat16 at the output)
     :param precompute_dtype: float64 (default) or float32 for the window tables (:58-59)
     """
     assert (filters_n % 2) == 0, "number of filters used in mdct transformation needs to be even"
@@ -29,7 +31,8 @@ class MDCTransformer:
     self.window_type = window_type
     self.compute_dtype = normalise_compute_dtype(compute_dtype, "MDCTransformer")
     self._dtype = torch_dtype(self.compute_dtype)
-    self._sfx = "f64" if self.compute_dtype == "float64" else "f32"
+    self._sfx = {"float64": "f64", "bfloat16": "bf16"}.get(self.compute_dtype, "f32")
+    self._bf16 = self.compute_dtype == "bfloat16"
     self._precompute_f32 = int(normalise_precompute_dtype(precompute_dtype) == "float32")
     kind = window_type.lower()   # window_type=None fails here exactly like the reference (:199)
     self._window_code = {"sine": _capi.WINDOW_SINE, "vorbis": _capi.WINDOW_VORBIS}.get(kind, _capi.WINDOW_ONES)
@@ -61,6 +64,8 @@ class MDCTransformer:
       H_inv[0, h - 1 - p, n - 1 - p] = self._unfold[:, 2]
       H_inv[1, h + p, n - 1 - p] = self._unfold[:, 3]
       self._dense = (torch.from_numpy(H.astype(np.float32)), torch.from_numpy(H_inv.astype(np.float32)))
+      if self._bf16:       # tf.cast(H, bfloat16) (:58-59)
+        self._dense = tuple(t.to(torch.bfloat16) for t in self._dense)
     return self._dense
 
   @property
@@ -78,8 +83,9 @@ class MDCTransformer:
     if plan is None:
       handle = ctypes.c_void_p()
       with torch.cuda.device(index):
-        _capi.check(_capi.lib().ac_mdct_plan_create(self.filters_n, self._window_code, self._precompute_f32,
-                                                    ctypes.byref(handle)))
+        _capi.check(_capi.lib().ac_mdct_plan_create_ex(self.filters_n, self._window_code, self._precompute_f32,
+                                                       _capi.DTYPE_BF16 if self._bf16 else _capi.DTYPE_F32,
+                                                       ctypes.byref(handle)))
       plan = self._plans[index] = handle
     return plan
 
@@ -107,7 +113,11 @@ class MDCTransformer:
     y = torch.empty((b, s // self.filters_n + 1, self.filters_n, c), dtype=self._dtype, device=x.device)
     with torch.cuda.device(x.device):
       forward = getattr(_capi.lib(), "ac_mdct_forward_" + self._sfx)
-      _capi.check(forward(self._plan(x.device), x.data_ptr(), y.data_ptr(), b, s, c, stream_ptr(x.device)))
+      if self._bf16:
+        work = bf16_workspace(_capi.lib(), x.numel(), y.numel(), x.device)
+        _capi.check(forward(self._plan(x.device), x.data_ptr(), y.data_ptr(), b, s, c, work.data_ptr(), stream_ptr(x.device)))
+      else:
+        _capi.check(forward(self._plan(x.device), x.data_ptr(), y.data_ptr(), b, s, c, stream_ptr(x.device)))
     return back(y)
 
   def inverse_transform(self, mdct_amplitudes):
@@ -123,7 +133,11 @@ class MDCTransformer:
     x = torch.empty((b, (m + 1) * n, c), dtype=self._dtype, device=y.device)
     with torch.cuda.device(y.device):
       inverse = getattr(_capi.lib(), "ac_mdct_inverse_" + self._sfx)
-      _capi.check(inverse(self._plan(y.device), y.data_ptr(), x.data_ptr(), b, m, c, stream_ptr(y.device)))
+      if self._bf16:
+        work = bf16_workspace(_capi.lib(), y.numel(), x.numel(), y.device)
+        _capi.check(inverse(self._plan(y.device), y.data_ptr(), x.data_ptr(), b, m, c, work.data_ptr(), stream_ptr(y.device)))
+      else:
+        _capi.check(inverse(self._plan(y.device), y.data_ptr(), x.data_ptr(), b, m, c, stream_ptr(y.device)))
     return back(x)
 
   def inverse_transform_compact(self, q, bark_thr, psychoacoustic, thr_scale=1.0):

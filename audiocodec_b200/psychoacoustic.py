@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _capi
-from ._tensors import torch_dtype, adopt, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr
+from ._tensors import torch_dtype, adopt, bf16_workspace, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr
 
 
 class PsychoacousticModel:
@@ -20,7 +20,10 @@ class PsychoacousticModel:
     """Same arguments as the reference (psychoacoustic.py:14-15).
 
     :raises TypeError: compute_dtype outside {float64, float32, bfloat16} (:42-43)
-    :raises NotImplementedError: bfloat16 compute (float32 is the tuned path, float64 runs functional kernels)
+
+    float32 is the tuned path, float64 runs functional kernels, bfloat16 runs the float32 kernels on bfloat16 tensors
+    with W, W_inv, the quiet threshold, the spreading matrix, eps, alpha and 1 / alpha cast to bfloat16 as in the
+    reference (:56, 65-69, 197, 206-208); the quantiser and add_noise are float32 / float64 only.
     """
     self.alpha = alpha
     self.sample_rate = sample_rate
@@ -29,6 +32,7 @@ class PsychoacousticModel:
     self.compute_dtype = normalise_compute_dtype(compute_dtype, "PsychoacousticModel")
     self._dtype = torch_dtype(self.compute_dtype)
     self._f64 = self.compute_dtype == "float64"
+    self._bf16 = self.compute_dtype == "bfloat16"
     if normalise_precompute_dtype(precompute_dtype) != "float64":
       raise NotImplementedError("PsychoacousticModel tables are precomputed in float64")
 
@@ -50,6 +54,10 @@ class PsychoacousticModel:
     self.W_inv = torch.from_numpy(w_inv)                                           # [nb, N]      (:67)
     self.quiet_threshold_intensity = torch.from_numpy(quiet).reshape(1, 1, nb, 1)  # (:68)
     self.spreading_matrix = torch.from_numpy(spreading)                            # [nb, nb]     (:69)
+    if self._bf16:       # tf.cast(..., compute_dtype) (:66-69)
+      self.W, self.W_inv = self.W.to(torch.bfloat16), self.W_inv.to(torch.bfloat16)
+      self.quiet_threshold_intensity = self.quiet_threshold_intensity.to(torch.bfloat16)
+      self.spreading_matrix = self.spreading_matrix.to(torch.bfloat16)
     self._plans = {}
 
   # ---- plans ------------------------------------------------------------------------------------------
@@ -59,8 +67,10 @@ class PsychoacousticModel:
     if plan is None:
       handle = ctypes.c_void_p()
       with torch.cuda.device(index):
-        _capi.check(_capi.lib().ac_pa_plan_create(float(self.sample_rate), self.filter_bands_n, self.bark_bands_n,
-                                                  float(self.alpha), ctypes.byref(handle)))
+        _capi.check(_capi.lib().ac_pa_plan_create_ex(float(self.sample_rate), self.filter_bands_n, self.bark_bands_n,
+                                                     float(self.alpha),
+                                                     _capi.DTYPE_BF16 if self._bf16 else _capi.DTYPE_F32,
+                                                     ctypes.byref(handle)))
       plan = self._plans[index] = handle
     return plan
 
@@ -75,15 +85,31 @@ class PsychoacousticModel:
     if a.dim() != 4 or a.shape[2] != self.filter_bands_n:
       raise ValueError(f"{name} must be [batches_n, blocks_n, {self.filter_bands_n}, channels_n], got {tuple(a.shape)}")
 
-  # ---- utilities (thin element-wise helpers; not part of the accelerated path) -------------------------
+  # ---- utilities ---------------------------------------------------------------------------------------
+  def _to_db(self, mdct_amplitude, normalised):
+    """One element-wise kernel (ac_pa_amplitude_to_db_f32 / _f64) for device tensors; python scalars and host tensors
+    (the reference calls it on a constant in __init__, :58) take the same formula on the host."""
+    if isinstance(mdct_amplitude, torch.Tensor) and mdct_amplitude.is_cuda or \
+        (not isinstance(mdct_amplitude, (torch.Tensor, np.ndarray, float, int)) and hasattr(mdct_amplitude, "__dlpack__")):
+      a, back = adopt(mdct_amplitude, "mdct_amplitude", dtype=self._dtype)
+      work = a.float() if self._bf16 else a             # bfloat16: the float32 kernel between two casts
+      out = torch.empty_like(work)
+      with torch.cuda.device(a.device):
+        fn = _capi.lib().ac_pa_amplitude_to_db_f64 if self._f64 else _capi.lib().ac_pa_amplitude_to_db_f32
+        _capi.check(fn(self._plan(a.device), work.data_ptr(), out.data_ptr(), work.numel(), int(normalised),
+                       stream_ptr(a.device)))
+      return back(out.to(self._dtype))
+    a = torch.as_tensor(mdct_amplitude, dtype=torch.float64 if self._f64 else torch.float32)
+    db = 10. * torch.log(torch.clamp_min(a ** 2.0, self._INTENSITY_EPS)) / math.log(10.) + self._dB_MAX
+    return (db - self._dB_MIN) / (self._dB_MAX - self._dB_MIN) if normalised else db
+
   def amplitude_to_dB(self, mdct_amplitude):
-    """psychoacoustic.py:71-85."""
-    a = torch.as_tensor(mdct_amplitude, dtype=torch.float32)
-    return 10. * torch.log(torch.clamp_min(a ** 2.0, self._INTENSITY_EPS)) / math.log(10.) + self._dB_MAX
+    """psychoacoustic.py:71-85: 10 log10(max(eps, a^2)) + 120, in [_dB_MIN, _dB_MAX]."""
+    return self._to_db(mdct_amplitude, False)
 
   def amplitude_to_dB_norm(self, mdct_amplitude):
-    """psychoacoustic.py:87-100."""
-    return (self.amplitude_to_dB(mdct_amplitude) - self._dB_MIN) / (self._dB_MAX - self._dB_MIN)
+    """psychoacoustic.py:87-100: the same on the normalised scale [0, 1]."""
+    return self._to_db(mdct_amplitude, True)
 
   @staticmethod
   def freq2bark(frequencies):
@@ -107,8 +133,13 @@ class PsychoacousticModel:
     b, m, _, c = a.shape
     ton = torch.empty((b, m, 1, c), dtype=self._dtype, device=a.device)
     with torch.cuda.device(a.device):
-      tonality = _capi.lib().ac_pa_tonality_f64 if self._f64 else _capi.lib().ac_pa_tonality_f32
-      _capi.check(tonality(self._plan(a.device), a.data_ptr(), ton.data_ptr(), b, m, c, stream_ptr(a.device)))
+      if self._bf16:
+        work = bf16_workspace(_capi.lib(), a.numel(), ton.numel(), a.device)
+        _capi.check(_capi.lib().ac_pa_tonality_bf16(self._plan(a.device), a.data_ptr(), ton.data_ptr(), b, m, c,
+                                                    work.data_ptr(), stream_ptr(a.device)))
+      else:
+        tonality = _capi.lib().ac_pa_tonality_f64 if self._f64 else _capi.lib().ac_pa_tonality_f32
+        _capi.check(tonality(self._plan(a.device), a.data_ptr(), ton.data_ptr(), b, m, c, stream_ptr(a.device)))
     return back(ton)
 
   def global_masking_threshold(self, mdct_amplitudes, tonality_per_block, drown=0.0):
@@ -130,14 +161,19 @@ class PsychoacousticModel:
       ton_ptr = ton.data_ptr()
     thr = torch.empty_like(a)
     with torch.cuda.device(a.device):
-      threshold = _capi.lib().ac_pa_threshold_f64 if self._f64 else _capi.lib().ac_pa_threshold_f32
-      _capi.check(threshold(self._plan(a.device), a.data_ptr(), ton_ptr, float(drown), thr.data_ptr(), b, m, c,
-                            stream_ptr(a.device)))
+      if self._bf16:
+        work = bf16_workspace(_capi.lib(), a.numel() + ((b * m * c + 3) & ~3), a.numel(), a.device)
+        _capi.check(_capi.lib().ac_pa_threshold_bf16(self._plan(a.device), a.data_ptr(), ton_ptr, float(drown),
+                                                     thr.data_ptr(), b, m, c, work.data_ptr(), stream_ptr(a.device)))
+      else:
+        threshold = _capi.lib().ac_pa_threshold_f64 if self._f64 else _capi.lib().ac_pa_threshold_f32
+        _capi.check(threshold(self._plan(a.device), a.data_ptr(), ton_ptr, float(drown), thr.data_ptr(), b, m, c,
+                              stream_ptr(a.device)))
     return back(thr)
 
   def add_noise(self, mdct_amplitudes, masking_threshold, seed=None):
     """mdct_amplitudes + masking_threshold * N(0, 1/6) (psychoacoustic.py:150-167), Philox counter RNG."""
-    if self._f64:
+    if self._f64 or self._bf16:
       raise NotImplementedError("add_noise is built for float32 only")
     a, back = adopt(mdct_amplitudes, "mdct_amplitudes")
     thr, _ = adopt(masking_threshold, "masking_threshold")
@@ -154,6 +190,8 @@ class PsychoacousticModel:
   # ---- quantiser (build-defined: the reference has none) ---------------------------
   def quantize(self, mdct_amplitudes, masking_threshold):
     """q = rint(A / thr), int32 (IEEE divide, round-half-even)."""
+    if self._bf16:
+      raise NotImplementedError("the quantiser (build-defined, no reference symbol) is built for float32 and float64")
     a, _ = adopt(mdct_amplitudes, "mdct_amplitudes", dtype=self._dtype)
     thr, _ = adopt(masking_threshold, "masking_threshold", dtype=self._dtype)
     if a.shape != thr.shape:
@@ -166,6 +204,8 @@ class PsychoacousticModel:
 
   def dequantize(self, q, masking_threshold):
     """A_hat = q * thr."""
+    if self._bf16:
+      raise NotImplementedError("the quantiser (build-defined, no reference symbol) is built for float32 and float64")
     q, _ = adopt(q, "q", dtype=torch.int32)
     thr, back = adopt(masking_threshold, "masking_threshold", dtype=self._dtype)
     if q.shape != thr.shape:
@@ -181,6 +221,8 @@ class PsychoacousticModel:
 
     :return: (q int32, step float32) with step = thr_scale * threshold, or q alone.
     """
+    if self._bf16:
+      raise NotImplementedError("the quantiser (build-defined, no reference symbol) is built for float32 and float64")
     if self._f64:                             # no fused float64 kernel: threshold (internal tonality), then quantise
       if float(thr_scale) != 1.0:
         raise NotImplementedError("thr_scale != 1 is built for float32 only")

@@ -46,6 +46,11 @@ typedef enum ac_window {     /* mdctransformer.py:199-211 */
   AC_WINDOW_VORBIS = 2
 } ac_window;
 
+typedef enum ac_compute_dtype {   /* compute_dtype of the two reference classes (mdctransformer.py:13, psychoacoustic.py:14) */
+  AC_DTYPE_F32 = 0,                /* tf.float32 (default); float64 tensors run on the same plans through the _f64 entry points */
+  AC_DTYPE_BF16 = 1                /* tf.bfloat16: tables and constants rounded to bfloat16, see the _bf16 entry points */
+} ac_compute_dtype;
+
 typedef struct ac_mdct_plan ac_mdct_plan;
 typedef struct ac_pa_plan ac_pa_plan;
 struct DLManagedTensor;      /* dlpack.h, DLPack v0.x ABI (the capsule named "dltensor") */
@@ -83,6 +88,9 @@ int ac_pa_mma_jobs_host(double sample_rate, int filter_bands_n, int bark_bands_n
 /* MDCTransformer.__init__ (mdctransformer.py:13-59).  filters_n must be even (AC_ERR_INVALID otherwise,
  * the reference asserts at :26).  Tables go to the current device. */
 int ac_mdct_plan_create(int filters_n, int window_type, int precompute_f32, ac_mdct_plan** out);
+/* The same with the compute dtype: AC_DTYPE_BF16 casts H / H_inv and the scale constants to bfloat16 as
+ * MDCTransformer(compute_dtype=tf.bfloat16) does (mdctransformer.py:58-59, 125, 145, 347). */
+int ac_mdct_plan_create_ex(int filters_n, int window_type, int precompute_f32, int compute_dtype, ac_mdct_plan** out);
 int ac_mdct_plan_destroy(ac_mdct_plan* plan);
 
 /* MDCTransformer.transform (mdctransformer.py:61-125):  x [B, S, C] -> y [B, S/N + 1, N, C].
@@ -102,6 +110,10 @@ int ac_mdct_inverse_dequant_f32(const ac_mdct_plan* plan, const int32_t* q, cons
 /* ---------------------------------------------------------------------------------- psychoacoustics */
 /* PsychoacousticModel.__init__ (psychoacoustic.py:14-69); compute dtype fp32, precompute float64. */
 int ac_pa_plan_create(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha, ac_pa_plan** out);
+/* The same with the compute dtype: AC_DTYPE_BF16 casts W, W_inv, the quiet threshold, the spreading matrix, the
+ * bark-axis linspace, eps, alpha and 1 / alpha to bfloat16 (psychoacoustic.py:56, 65-69, 187-189, 197, 206-208). */
+int ac_pa_plan_create_ex(double sample_rate, int filter_bands_n, int bark_bands_n, double alpha, int compute_dtype,
+                         ac_pa_plan** out);
 int ac_pa_plan_destroy(ac_pa_plan* plan);
 
 /* PsychoacousticModel.tonality (psychoacoustic.py:102-120):  y [B, M, N, C] -> ton [B, M, 1, C]. */
@@ -180,6 +192,31 @@ int ac_pa_threshold_f64(const ac_pa_plan* plan, const double* y, const double* t
                         int64_t batches, int64_t blocks, int channels, void* stream);
 int ac_quantize_f64(const double* y, const double* thr, int32_t* q, int64_t n, void* stream);
 int ac_dequantize_f64(const int32_t* q, const double* thr, double* y, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------ bfloat16 compute dtype */
+/* compute_dtype=tf.bfloat16 (psychoacoustic.py:42-44; mdctransformer.py:326-344 up-casts to float32 around the DCT):
+ * tensors are bfloat16 at the boundary (void* = device pointers to bfloat16), the plan (created with AC_DTYPE_BF16)
+ * holds bfloat16-valued tables and constants, and the arithmetic in between runs in float32 - the reference's rule for
+ * the DCT applied to the whole path; TensorFlow's per-op rounding of intermediates to bfloat16 is NOT reproduced
+ * (it cannot be pinned without TensorFlow; the result is the closer one to the float64 value).  The float32 copies of
+ * inputs and outputs live in `workspace`: device memory of ac_bf16_workspace_bytes(input elements, output elements)
+ * bytes (for ac_pa_threshold_bf16 the inputs are the amplitudes plus, padded to a multiple of 4, the tonality).
+ * Functional path (three launches), not tuned: the north star is float32. */
+int64_t ac_bf16_workspace_bytes(int64_t in_elems, int64_t out_elems);
+int ac_mdct_forward_bf16(const ac_mdct_plan* plan, const void* x, void* y,
+                         int64_t batches, int64_t samples, int channels, void* workspace, void* stream);
+int ac_mdct_inverse_bf16(const ac_mdct_plan* plan, const void* y, void* x,
+                         int64_t batches, int64_t blocks, int channels, void* workspace, void* stream);
+int ac_pa_tonality_bf16(const ac_pa_plan* plan, const void* y, void* ton,
+                        int64_t batches, int64_t blocks, int channels, void* workspace, void* stream);
+int ac_pa_threshold_bf16(const ac_pa_plan* plan, const void* y, const void* ton, float drown, void* thr,
+                         int64_t batches, int64_t blocks, int channels, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------ dB utilities */
+/* PsychoacousticModel.amplitude_to_dB (psychoacoustic.py:71-85): out = 10 ln(max(eps, a^2)) / ln 10 + 120;
+ * normalised != 0: amplitude_to_dB_norm (:87-100), (dB - dB_MIN) / (dB_MAX - dB_MIN) in [0, 1].  n elements. */
+int ac_pa_amplitude_to_db_f32(const ac_pa_plan* plan, const float* a, float* out, int64_t n, int normalised, void* stream);
+int ac_pa_amplitude_to_db_f64(const ac_pa_plan* plan, const double* a, double* out, int64_t n, int normalised, void* stream);
 
 /* ------------------------------------------------------------------------- host-buffer streaming */
 /* encode + decode of clips that live in HOST memory (the call a file / network front end makes; no reference

@@ -19,7 +19,9 @@ restatement is checked against those fixtures and against the reference's tests 
 tests/test_oracle.py.  Real TensorFlow was never available (not installable offline), so the TF kernels
 themselves (Eigen conv, FFT-based DCT, einsum) are represented by their documented semantics.
 
-Two arithmetic modes, selected by `compute_dtype`:
+Three arithmetic modes, selected by `compute_dtype`:
+  * "bfloat16"  - every op rounds its result to bfloat16 (ml_dtypes), contractions / reductions accumulate in float32,
+    the DCT runs in float32 (mdctransformer.py:326-344).  UNPINNED: TensorFlow's own bfloat16 kernels were never run.
   * np.float64  - "truth": every op in double (what the reference computes with compute_dtype=tf.float64)
   * np.float32  - "fp32-faithful": tables built in float64 then cast (mdctransformer.py:58-59,
     psychoacoustic.py:65-69), data-path arithmetic in float32 like the reference's default graph.
@@ -33,8 +35,27 @@ import scipy.fft
 __all__ = ["MDCTransformer", "PsychoacousticModel", "quantize", "dequantize", "synthetic_audio"]
 
 
+def _bfloat16():
+  import ml_dtypes          # numpy ufuncs on ml_dtypes.bfloat16 compute in float32 and round: TF's per-op rounding
+  return ml_dtypes.bfloat16
+
+
 def _as_np_dtype(dtype):
+  if isinstance(dtype, str) and dtype in ("bfloat16", "bf16"):
+    return _bfloat16()
   return np.dtype(dtype).type
+
+
+def _is_bf16(ct):
+  return np.dtype(ct).name == "bfloat16"
+
+
+def _einsum(ct, spec, *ops):
+  """np.einsum in the compute dtype; bfloat16 operands are contracted with float32 accumulation and rounded once, which is
+  how TF's CPU kernels (Eigen) run a bfloat16 contraction or reduction."""
+  if _is_bf16(ct):
+    return np.einsum(spec, *[np.asarray(o, dtype=np.float32) for o in ops]).astype(ct)
+  return np.einsum(spec, *ops).astype(ct)
 
 
 # ================================================================================================ MDCT
@@ -105,6 +126,11 @@ class MDCTransformer:
     The reference reaches it through a zero-interleaved DCT-III (:333-347); the transform computed is the
     same.  SciPy evaluates it in the dtype of `u` (float32 stays float32).
     """
+    if _is_bf16(u.dtype):
+      # up-cast to float32 (:326-330), DCT-III of the zero-interleaved signal = DCT-IV / sqrt(2), down-cast (:340-344),
+      # then the bfloat16 constant sqrt(2) (:347)
+      y = (scipy.fft.dct(u.astype(np.float32), type=4, norm='ortho', axis=-1) / np.float32(math.sqrt(2.0))).astype(u.dtype)
+      return (np.sqrt(u.dtype.type(2.)) * y).astype(u.dtype)
     return scipy.fft.dct(u, type=4, norm='ortho', axis=-1).astype(u.dtype)
 
   def transform(self, x):
@@ -145,6 +171,11 @@ def _polymatmul(a, f):
   """
   blocks = a.shape[1]
   taps = f.shape[0]
+  if _is_bf16(a.dtype):      # one convolution op: float32 accumulation over both taps, one rounding
+    out = np.zeros((a.shape[0], blocks + taps - 1, f.shape[2]), dtype=np.float32)
+    for t in range(taps):
+      out[:, t:t + blocks, :] += np.matmul(a.astype(np.float32), f[t].astype(np.float32))
+    return out.astype(a.dtype)
   out = np.zeros((a.shape[0], blocks + taps - 1, f.shape[2]), dtype=np.result_type(a, f))
   for t in range(taps):
     out[:, t:t + blocks, :] += np.matmul(a, f[t])
@@ -162,8 +193,8 @@ class PsychoacousticModel:
     self.bark_bands_n = int(bark_bands_n)
     self.filter_bands_n = int(filter_bands_n)
     ct = _as_np_dtype(compute_dtype)
-    if ct not in (np.float64, np.float32):
-      raise TypeError("oracle supports float64 and float32 compute (reference also lists bfloat16, :42-43)")
+    if ct not in (np.float64, np.float32) and not _is_bf16(ct):
+      raise TypeError("compute_dtype should be float64, float32 or bfloat16 (:42-43)")
     self.compute_dtype = ct
     pd = _as_np_dtype(precompute_dtype)
 
@@ -249,8 +280,9 @@ class PsychoacousticModel:
     ct = self.compute_dtype
     a = self._check(mdct_amplitudes)
     intensity = np.power(a, ct(2))                                            # (:113)
-    log_gm = np.mean(np.log(np.maximum(self._INTENSITY_EPS, intensity)), axis=2, keepdims=True, dtype=ct)
-    am = np.mean(intensity, axis=2, keepdims=True, dtype=ct) + self._INTENSITY_EPS
+    acc = np.float32 if _is_bf16(ct) else ct          # a bfloat16 reduction accumulates in float32 and rounds once
+    log_gm = np.mean(np.log(np.maximum(self._INTENSITY_EPS, intensity)), axis=2, keepdims=True, dtype=acc).astype(ct)
+    am = np.mean(intensity, axis=2, keepdims=True, dtype=acc).astype(ct) + self._INTENSITY_EPS
     sfm = ct(10.) * np.log(np.exp(log_gm) / am) / ct(math.log(10.0))          # (:114-116)
     return np.minimum(sfm / ct(-60.), ct(1.0)).astype(ct)                     # (:118)
 
@@ -278,7 +310,7 @@ class PsychoacousticModel:
     lin = (np.arange(nb).astype(ct) * (stop / ct(nb - 1))).astype(ct) if nb > 1 else np.zeros(1, ct)
     if nb > 1:
       lin[-1] = stop
-    offset = ct(1. - drown) * (np.einsum('nbic,j->nbjc', ton, lin) + ct(9.) * ton + ct(5.5))   # (:185-191)
+    offset = ct(1. - drown) * (_einsum(ct, 'nbic,j->nbjc', ton, lin) + ct(9.) * ton + ct(5.5))   # (:185-191)
     return np.power(ct(10.0), ct(-self.alpha) * offset / ct(10.0)).astype(ct)                  # (:197)
 
   def _masking_intensity_in_bark(self, mdct_amplitudes, tonality_per_block, drown=0.0):
@@ -292,29 +324,29 @@ class PsychoacousticModel:
     gain = self.masking_offset_factor(tonality_per_block, drown)
     bark = self._to_bark_intensity(mdct_amplitudes)                                        # (:204)
     p = np.power(np.maximum(self._INTENSITY_EPS, bark), ct(self.alpha))                    # (:206)
-    spread = np.einsum('nbic,ij->nbjc', p, self.spreading_matrix).astype(ct) * gain        # (:205-207)
+    spread = _einsum(ct, 'nbic,ij->nbjc', p, self.spreading_matrix) * gain        # (:205-207)
     return np.power(np.maximum(self._INTENSITY_EPS, spread), ct(1. / self.alpha)).astype(ct)   # (:208)
 
   def _masking_intensity_dense(self, mdct_amplitudes, tonality_per_block, drown=0.0):
     """Literal form of psychoacoustic.py:195-208 (materialised 5-D masking matrix); small inputs only."""
     ct = self.compute_dtype
     gain = self.masking_offset_factor(tonality_per_block, drown)
-    masking_matrix = np.einsum('ij,nbjc->nbijc', self.spreading_matrix, gain)              # (:195)
+    masking_matrix = _einsum(ct, 'ij,nbjc->nbijc', self.spreading_matrix, gain)              # (:195)
     bark = self._to_bark_intensity(mdct_amplitudes)
     p = np.power(np.maximum(self._INTENSITY_EPS, bark), ct(self.alpha))
-    spread = np.einsum('nbic,nbijc->nbjc', p, masking_matrix).astype(ct)                   # (:205)
+    spread = _einsum(ct, 'nbic,nbijc->nbjc', p, masking_matrix)                   # (:205)
     return np.power(np.maximum(self._INTENSITY_EPS, spread), ct(1. / self.alpha)).astype(ct)
 
   def _to_bark_intensity(self, mdct_amplitudes):
     """I_bark = A^2 . W  (psychoacoustic.py:301-315)."""
     ct = self.compute_dtype
     a = self._check(mdct_amplitudes)
-    return np.einsum('nbic,ij->nbjc', np.power(a, ct(2)), self.W).astype(ct)               # (:312-313)
+    return _einsum(ct, 'nbic,ij->nbjc', np.power(a, ct(2)), self.W)               # (:312-313)
 
   def _bark_intensity_to_freq_ampl(self, bark_intensity):
     """sqrt(max(eps, I_bark . W_inv))  (psychoacoustic.py:317-331)."""
     ct = self.compute_dtype
-    spread = np.einsum('nbic,ij->nbjc', bark_intensity, self.W_inv).astype(ct)             # (:330)
+    spread = _einsum(ct, 'nbic,ij->nbjc', bark_intensity, self.W_inv)             # (:330)
     return np.power(np.maximum(self._INTENSITY_EPS, spread), ct(0.5)).astype(ct)           # (:331)
 
   def _check(self, a):

@@ -80,8 +80,9 @@ def test_constructor_errors_match_reference():
     audiocodec_b200.MDCTransformer(8, window_type=None)        # mdctransformer.py:199 (.lower() on None)
   with pytest.raises(TypeError):
     audiocodec_b200.PsychoacousticModel(44100, compute_dtype='float16')   # psychoacoustic.py:42-43
-  with pytest.raises(NotImplementedError):
-    audiocodec_b200.PsychoacousticModel(44100, compute_dtype='bfloat16')
+  bf = audiocodec_b200.PsychoacousticModel(44100, 64, compute_dtype='bfloat16')      # accepted, as in the reference
+  assert bf.compute_dtype == "bfloat16" and bf.W.dtype == torch.bfloat16 and bf.spreading_matrix.dtype == torch.bfloat16
+  assert audiocodec_b200.MDCTransformer(8, compute_dtype=torch.bfloat16).H.dtype == torch.bfloat16
   with pytest.raises(TypeError):
     audiocodec_b200.MDCTransformer(8, compute_dtype='int32')
   assert audiocodec_b200.MDCTransformer(8, compute_dtype=torch.float32).compute_dtype == "float32"
