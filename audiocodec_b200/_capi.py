@@ -66,6 +66,13 @@ SIGNATURES = {
                                          _c_int64, ctypes.c_int, _c_void_p]),
   "ac_quantize_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
   "ac_dequantize_f64": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_void_p]),
+  "ac_pa_tonality_backward_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int,
+                                                 _c_void_p]),
+  "ac_pa_threshold_backward_f32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, ctypes.c_float, _c_void_p, _c_void_p,
+                                                  _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p]),
+  "ac_entropy_plan_i32": (ctypes.c_int, [_c_void_p, _c_int64, _c_int64, _c_void_p, _c_void_p]),
+  "ac_entropy_encode_i32": (ctypes.c_int, [_c_void_p, _c_int64, _c_int64, _c_void_p, _c_void_p, _c_void_p]),
+  "ac_entropy_decode_i32": (ctypes.c_int, [_c_void_p, _c_void_p, _c_int64, _c_int64, _c_void_p, _c_void_p]),
   "ac_bf16_workspace_bytes": (_c_int64, [_c_int64, _c_int64]),
   "ac_mdct_forward_bf16": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p, _c_void_p]),
   "ac_mdct_inverse_bf16": (ctypes.c_int, [_c_void_p, _c_void_p, _c_void_p, _c_int64, _c_int64, ctypes.c_int, _c_void_p, _c_void_p]),

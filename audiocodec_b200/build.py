@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIBDIR = os.path.join(PKG, "lib")
 LIBNAME = "libaudiocodec_b200.so"
-SOURCES = ["capi.cu", "mdct_kernels.cu", "mdct_tile_kernels.cu", "psycho_kernels.cu", "psycho_mma_kernels.cu", "f64_kernels.cu", "elementwise_kernels.cu", "tables.cpp"]
+SOURCES = ["capi.cu", "mdct_kernels.cu", "mdct_tile_kernels.cu", "psycho_kernels.cu", "psycho_mma_kernels.cu", "f64_kernels.cu", "elementwise_kernels.cu", "entropy_kernels.cu", "backward_kernels.cu", "tables.cpp"]
 HEADERS = ["kernels.h", "tables.h", "fft_core.cuh", "async_copy.cuh", "mdct_tile_core.cuh", os.path.join("..", "..", "include", "audiocodec_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--shared"]

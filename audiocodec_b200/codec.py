@@ -134,9 +134,52 @@ class AudioCodec:
   def __del__(self):
     self._drop_pipes()
 
+  # ---- entropy-coded bitstream (no reference symbol) -----------------------------------
+  def pack(self, q):
+    """q int32 [B, F, N, C] -> (stream uint8 [bytes + 4], offsets int64 [B F + 1]): adaptive Golomb-Rice, one
+    independent, 4-byte aligned byte range per frame (ac_entropy_plan_i32 + ac_entropy_encode_i32).  offsets[-1] is the
+    size of the stream in bytes; the four bytes behind it are read-ahead slack of the decoder."""
+    q, _ = adopt(q, "q", dtype=torch.int32)
+    if q.dim() != 4:
+      raise ValueError("q must be [batches_n, blocks_n, filters_n, channels_n]")
+    rows, row_len = q.shape[0] * q.shape[1], q.shape[2] * q.shape[3]
+    lib = _capi.lib()
+    with torch.cuda.device(q.device):
+      offsets = torch.empty(rows + 1, dtype=torch.int64, device=q.device)
+      _capi.check(lib.ac_entropy_plan_i32(q.data_ptr(), rows, row_len, offsets.data_ptr(), stream_ptr(q.device)))
+      total = int(offsets[-1].item())          # the one host read: the size of the allocation
+      stream = torch.zeros(total + 4, dtype=torch.uint8, device=q.device)
+      _capi.check(lib.ac_entropy_encode_i32(q.data_ptr(), rows, row_len, offsets.data_ptr(), stream.data_ptr(),
+                                            stream_ptr(q.device)))
+    return stream, offsets
+
+  def unpack(self, stream, offsets, shape):
+    """(stream, offsets) of pack -> q int32 of `shape` [B, F, N, C]."""
+    b, f, n, c = (int(v) for v in shape)
+    rows, row_len = b * f, n * c
+    if offsets.numel() != rows + 1 or offsets.dtype != torch.int64 or stream.dtype != torch.uint8:
+      raise ValueError("offsets must be int64 [rows + 1] and stream uint8")
+    q = torch.empty((b, f, n, c), dtype=torch.int32, device=stream.device)
+    with torch.cuda.device(stream.device):
+      _capi.check(_capi.lib().ac_entropy_decode_i32(stream.data_ptr(), offsets.data_ptr(), rows, row_len, q.data_ptr(),
+                                                    stream_ptr(stream.device)))
+    return q
+
+  def stream_bytes(self, q):
+    """Size in bytes of the entropy-coded stream pack(q) would write (ac_entropy_plan_i32 alone: sizes and offsets)."""
+    q, _ = adopt(q, "q", dtype=torch.int32)
+    rows, row_len = q.shape[0] * q.shape[1], q.shape[2] * q.shape[3]
+    if row_len % 16 != 0 or rows == 0:
+      return 0
+    with torch.cuda.device(q.device):
+      offsets = torch.empty(rows + 1, dtype=torch.int64, device=q.device)
+      _capi.check(_capi.lib().ac_entropy_plan_i32(q.data_ptr(), rows, row_len, offsets.data_ptr(), stream_ptr(q.device)))
+    return int(offsets[-1].item())
+
   def stats(self, q):
     """Per-shard bitstream statistics gathered across ranks at the end of a job: a device tensor
-    [coefficients, non-zero integers, sum log2(2|q|+1)], counted by the library's own kernel (ac_codec_stats_i32)."""
+    [coefficients, non-zero integers, sum log2(2|q|+1), bytes of the entropy-coded stream], counted by the library's
+    own kernels (ac_codec_stats_i32, ac_entropy_plan_i32)."""
     est = self.psychoacoustic.bit_estimate(q)
-    return torch.tensor([float(est["coefficients"]), float(est["nonzero"]), est["bits"]], dtype=torch.float64,
-                        device=q.device)
+    return torch.tensor([float(est["coefficients"]), float(est["nonzero"]), est["bits"], float(self.stream_bytes(q))],
+                        dtype=torch.float64, device=q.device)

@@ -1157,6 +1157,60 @@ int ac_dequantize_f64(const int32_t* q, const double* thr, double* y, int64_t n,
   return err == cudaSuccess ? AC_OK : cuda_fail(err, "dequantize_f64 launch");
 }
 
+// ------------------------------------------------------------------------------------------- backward pass
+int ac_pa_tonality_backward_f32(const ac_pa_plan* plan, const float* y, const float* grad_ton, float* grad_y,
+                                int64_t batches, int64_t blocks, int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (batches * blocks == 0) return AC_OK;
+  if (y == nullptr || grad_ton == nullptr || grad_y == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::pa_tonality_backward(plan->tb, y, grad_ton, grad_y, batches * blocks, channels,
+                                             static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_tonality_backward launch");
+}
+
+int ac_pa_threshold_backward_f32(const ac_pa_plan* plan, const float* y, const float* ton, float drown, const float* grad_thr,
+                                 float* grad_y, float* grad_ton, int64_t batches, int64_t blocks, int channels, void* stream) {
+  if (int rc = check_common(plan, batches, blocks, channels)) return rc;
+  if (batches * blocks == 0) return AC_OK;
+  if (y == nullptr || ton == nullptr || grad_thr == nullptr || grad_y == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::pa_threshold_backward(plan->tb, y, ton, drown, grad_thr, grad_y, grad_ton, batches * blocks, channels,
+                                              static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "pa_threshold_backward launch");
+}
+
+// ----------------------------------------------------------------------------------- entropy-coded bitstream
+static int entropy_args(int64_t rows, int64_t row_len) {
+  if (rows < 0 || row_len < 16 || row_len % 16 != 0 || row_len > (1 << 24))
+    return fail(AC_ERR_INVALID, "rows >= 0 and row_len a multiple of 16 in [16, 2^24] expected (got %lld rows of %lld)",
+                (long long)rows, (long long)row_len);
+  return AC_OK;
+}
+
+int ac_entropy_plan_i32(const int32_t* q, int64_t rows, int64_t row_len, int64_t* offsets, void* stream) {
+  if (int rc = entropy_args(rows, row_len)) return rc;
+  if (offsets == nullptr || (q == nullptr && rows > 0)) return fail(AC_ERR_INVALID, "null tensor");
+  cudaError_t err = ac::entropy_plan(q, rows, static_cast<int>(row_len), offsets, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "entropy_plan launch");
+}
+
+int ac_entropy_encode_i32(const int32_t* q, int64_t rows, int64_t row_len, const int64_t* offsets, uint8_t* bytes, void* stream) {
+  if (int rc = entropy_args(rows, row_len)) return rc;
+  if (rows == 0) return AC_OK;
+  if (q == nullptr || offsets == nullptr || bytes == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  if (reinterpret_cast<uintptr_t>(bytes) & 3) return fail(AC_ERR_INVALID, "the stream buffer must be 4-byte aligned");
+  cudaError_t err = ac::entropy_encode(q, rows, static_cast<int>(row_len), offsets, bytes, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "entropy_encode launch");
+}
+
+int ac_entropy_decode_i32(const uint8_t* bytes, const int64_t* offsets, int64_t rows, int64_t row_len, int32_t* q, void* stream) {
+  if (int rc = entropy_args(rows, row_len)) return rc;
+  if (rows == 0) return AC_OK;
+  if (q == nullptr || offsets == nullptr || bytes == nullptr) return fail(AC_ERR_INVALID, "null tensor");
+  if (reinterpret_cast<uintptr_t>(bytes) & 3) return fail(AC_ERR_INVALID, "the stream buffer must be 4-byte aligned");
+  cudaError_t err = ac::entropy_decode(bytes, offsets, rows, static_cast<int>(row_len), q, static_cast<cudaStream_t>(stream));
+  return err == cudaSuccess ? AC_OK : cuda_fail(err, "entropy_decode launch");
+}
+
 // ------------------------------------------------------------------------------- bfloat16 compute dtype
 // Tensors are bfloat16 at the boundary, the plan's tables and constants are bfloat16 values (ac_*_plan_create_ex with
 // AC_DTYPE_BF16), the kernels run in float32 on float32 copies held in the caller's workspace: the reference's rule for

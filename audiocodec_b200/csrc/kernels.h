@@ -138,6 +138,22 @@ cudaError_t amplitude_to_db_f32(const float* a, float* out, int64_t n, float eps
 cudaError_t amplitude_to_db_f64(const double* a, double* out, int64_t n, double eps, double db_max, double db_min, bool norm,
                                 cudaStream_t stream);
 
+// backward_kernels.cu: vector-Jacobian products of tonality and global_masking_threshold (warp per item, functional)
+cudaError_t pa_tonality_backward(const PaDeviceTables& tb, const float* y, const float* grad_ton, float* grad_y,
+                                 int64_t rows, int channels, cudaStream_t stream);
+cudaError_t pa_threshold_backward(const PaDeviceTables& tb, const float* y, const float* ton, float drown,
+                                  const float* grad_thr, float* grad_y, float* grad_ton, int64_t rows, int channels,
+                                  cudaStream_t stream);
+
+// entropy_kernels.cu: adaptive Golomb-Rice bitstream of the quantised integers, one independent byte range per row of
+// row_len integers (row_len a multiple of 16).  entropy_plan: offsets[0 .. rows] = byte offset of every row, offsets[rows]
+// = size of the stream; entropy_encode writes it; entropy_decode reads it back (the stream buffer needs 4 bytes of slack).
+cudaError_t entropy_plan(const int32_t* q, int64_t rows, int row_len, int64_t* offsets, cudaStream_t stream);
+cudaError_t entropy_encode(const int32_t* q, int64_t rows, int row_len, const int64_t* offsets, uint8_t* bytes,
+                           cudaStream_t stream);
+cudaError_t entropy_decode(const uint8_t* bytes, const int64_t* offsets, int64_t rows, int row_len, int32_t* q,
+                           cudaStream_t stream);
+
 // float64 compute dtype (f64_kernels.cu): the same tables in double, sparse forms shared with the fp32 plan
 struct MdctDeviceTables64 {
   int n = 0;

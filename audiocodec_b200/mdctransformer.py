@@ -10,7 +10,7 @@ import ctypes
 import numpy as np
 import torch
 
-from . import _capi
+from . import _capi, autograd
 from ._tensors import adopt, bf16_workspace, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr, torch_dtype
 
 
@@ -104,6 +104,8 @@ class MDCTransformer:
     :return:  [batches_n, blocks_n + 1, filters_n, channels_n] with samples_n = blocks_n * filters_n
     :raises ValueError: samples_n is not a multiple of filters_n (the reference raises InvalidArgumentError, :287)
     """
+    if autograd.wants_grad(x) and self.compute_dtype == "float32":
+      return autograd.transform(self, x)          # differentiable layer (the reference's @tf.function, :61)
     x, back = adopt(x, "x", dtype=self._dtype)
     if x.dim() != 3:
       raise ValueError(f"x must be [batches_n, samples_n, channels_n], got shape {tuple(x.shape)}")
@@ -126,6 +128,8 @@ class MDCTransformer:
     :param mdct_amplitudes: [batches_n, blocks_n, filters_n, channels_n], float32, CUDA
     :return:                [batches_n, (blocks_n + 1) * filters_n, channels_n]
     """
+    if autograd.wants_grad(mdct_amplitudes) and self.compute_dtype == "float32":
+      return autograd.inverse_transform(self, mdct_amplitudes)
     y, back = adopt(mdct_amplitudes, "mdct_amplitudes", dtype=self._dtype)
     if y.dim() != 4 or y.shape[2] != self.filters_n:
       raise ValueError(f"mdct_amplitudes must be [batches_n, blocks_n, {self.filters_n}, channels_n], got {tuple(y.shape)}")

@@ -10,7 +10,7 @@ import math
 import numpy as np
 import torch
 
-from . import _capi
+from . import _capi, autograd
 from ._tensors import torch_dtype, adopt, bf16_workspace, normalise_compute_dtype, normalise_precompute_dtype, stream_ptr
 
 
@@ -128,6 +128,8 @@ class PsychoacousticModel:
     :param mdct_amplitudes: [batches_n, blocks_n, filter_bands_n, channels_n], float32, CUDA
     :return:                [batches_n, blocks_n, 1, channels_n]
     """
+    if autograd.wants_grad(mdct_amplitudes) and self.compute_dtype == "float32":
+      return autograd.tonality(self, mdct_amplitudes)      # differentiable layer (the reference's @tf.function, :102)
     a, back = adopt(mdct_amplitudes, "mdct_amplitudes", dtype=self._dtype)
     self._check_amplitudes(a)
     b, m, _, c = a.shape
@@ -150,6 +152,9 @@ class PsychoacousticModel:
     :param drown:              0..1, python float
     :return:                   [batches_n, blocks_n, filter_bands_n, channels_n], never below 1e-7
     """
+    if tonality_per_block is not None and self.compute_dtype == "float32" and \
+        autograd.wants_grad(mdct_amplitudes, tonality_per_block):
+      return autograd.global_masking_threshold(self, mdct_amplitudes, tonality_per_block, drown)
     a, back = adopt(mdct_amplitudes, "mdct_amplitudes", dtype=self._dtype)
     self._check_amplitudes(a)
     b, m, _, c = a.shape

@@ -484,6 +484,7 @@ def run_b200_arm(args):
       "kernels": per_kernel,
       "clocks": clocks,
       "stats": {"coefficients": stats[0].item(), "nonzero": stats[1].item(), "bits_estimate": stats[2].item(),
+                "stream_bytes": stats[3].item(), "bits_per_coefficient": 8.0 * stats[3].item() / max(stats[0].item(), 1.0),
                 "roundtrip_rms_error": err, "finite": ok},
     }
     line.update(extra)

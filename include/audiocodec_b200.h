@@ -193,6 +193,34 @@ int ac_pa_threshold_f64(const ac_pa_plan* plan, const double* y, const double* t
 int ac_quantize_f64(const double* y, const double* thr, int32_t* q, int64_t n, void* stream);
 int ac_dequantize_f64(const int32_t* q, const double* thr, double* y, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------- backward pass */
+/* The reference's methods are @tf.function graphs of differentiable ops (psychoacoustic.py:102, :122; the comment at
+ * :311 speaks of the gradient): these are the vector-Jacobian products that make the drop-in classes differentiable
+ * layers too.  grad_y [B, M, N, C] is written (not accumulated); grad_ton [B, M, 1, C] may be NULL.  Clamps
+ * (max(eps, .), min(., 1), the quiet-threshold branch) pass no gradient where they are active.  The MDCT needs no entry
+ * point: for the orthogonal windows (sine, vorbis) the adjoint of ac_mdct_forward_f32 is ac_mdct_inverse_f32 / 4N
+ * cropped by one block at both ends, and the adjoint of ac_mdct_inverse_f32 is 4N ac_mdct_forward_f32 without its
+ * first and last frame (audiocodec_b200/autograd.py). */
+int ac_pa_tonality_backward_f32(const ac_pa_plan* plan, const float* y, const float* grad_ton, float* grad_y,
+                                int64_t batches, int64_t blocks, int channels, void* stream);
+int ac_pa_threshold_backward_f32(const ac_pa_plan* plan, const float* y, const float* ton, float drown,
+                                 const float* grad_thr, float* grad_y, float* grad_ton,
+                                 int64_t batches, int64_t blocks, int channels, void* stream);
+
+/* ----------------------------------------------------------------------- entropy-coded bitstream */
+/* Adaptive Golomb-Rice coding of the quantised integers (no reference symbol - the reference has no quantiser and no
+ * bitstream; the format is build-defined: csrc/entropy_kernels.cu, restated bit for bit by
+ * oracle/entropy_oracle.py).  q is seen as `rows` rows of `row_len` integers (row_len a multiple of 16; the codec uses
+ * one frame = filters_n x channels_n); every row becomes an independent byte range of the stream that starts on a 4-byte
+ * boundary, so rows decode in parallel.  Per 16 values: a 5-bit Rice parameter (31 = all zero), then zigzag(q) as
+ * (u >> k) zeros, a one, k low bits.
+ *   ac_entropy_plan_i32   offsets[0 .. rows] (device, int64): byte offset of every row; offsets[rows] = stream size
+ *   ac_entropy_encode_i32 writes the stream into bytes (device, 4-byte aligned, offsets[rows] + 4 bytes)
+ *   ac_entropy_decode_i32 reads it back (reads up to 4 bytes behind the last row) */
+int ac_entropy_plan_i32(const int32_t* q, int64_t rows, int64_t row_len, int64_t* offsets, void* stream);
+int ac_entropy_encode_i32(const int32_t* q, int64_t rows, int64_t row_len, const int64_t* offsets, uint8_t* bytes, void* stream);
+int ac_entropy_decode_i32(const uint8_t* bytes, const int64_t* offsets, int64_t rows, int64_t row_len, int32_t* q, void* stream);
+
 /* ------------------------------------------------------------------------ bfloat16 compute dtype */
 /* compute_dtype=tf.bfloat16 (psychoacoustic.py:42-44; mdctransformer.py:326-344 up-casts to float32 around the DCT):
  * tensors are bfloat16 at the boundary (void* = device pointers to bfloat16), the plan (created with AC_DTYPE_BF16)

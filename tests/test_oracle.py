@@ -189,3 +189,16 @@ def test_quantizer_spec():
   assert q.dtype == np.int32
   assert q.tolist() == [0, 2, 2, 0, -2, 0, -3]          # round-half-to-even, like tf.round
   assert oracle.dequantize(q, 0.5 * thr).tolist() == [0, 1, 1, 0, -1, 0, -1.5]
+
+
+def test_entropy_restatement_round_trip():
+  """oracle/entropy_oracle.py (the CPU restatement of the build-defined bitstream): lossless, sizes consistent."""
+  from oracle import entropy_oracle as eo
+  rng = np.random.default_rng(11)
+  q = np.rint(rng.standard_normal((9, 96)) * rng.choice([0, 0.3, 2, 40, 3000], (9, 1))).astype(np.int32)
+  q[0] = 0
+  q[1, 5], q[2, 7] = 2 ** 31 - 1, -2 ** 31
+  stream, offsets = eo.encode(q)
+  assert np.array_equal(eo.decode(stream, offsets, 9, 96), q)
+  assert np.array_equal(np.diff(offsets), eo.row_sizes(q)) and np.all(np.diff(offsets) % 4 == 0)
+  assert offsets[1] - offsets[0] == 4 * ((6 * 5 + 31) // 32)            # an all-zero row: six 5-bit headers
