@@ -168,8 +168,17 @@ static bool build_mma_jobs(const ac::PaTables& t, ac::PaJobParams& jp, std::vect
   return false;
 }
 
+// instructions per lane of a step of four filters, of the tail of a job that completes / does not complete its band, and
+// of one filter of the tonality pass: what the split of a chunk's work between the eight warps is levelled by
+// (AC_PA_COST="step,final,partial,ton" overrides it when a plan is created: experiments)
+struct PaCostModel {
+  double step = 13.5, final = 45.0, partial = 25.0, ton_row = 9.0;
+};
+
 static bool build_mma_jobs_chunk(const ac::PaTables& t, ac::PaJobParams& jp, std::vector<float>& mma_w4, int* chunk_k,
                                  int* n_chunks_out, int* n_jobs_out, const int mma_chunk_k) {
+  PaCostModel cm;
+  if (const char* e = std::getenv("AC_PA_COST")) std::sscanf(e, "%lf,%lf,%lf,%lf", &cm.step, &cm.final, &cm.partial, &cm.ton_row);
   const int mma_n_chunks = (t.n + mma_chunk_k - 1) / mma_chunk_k;
   std::vector<int4> job_desc;
   std::vector<int32_t> job_start(static_cast<size_t>(mma_n_chunks) * 9 + 1, 0);
@@ -193,7 +202,7 @@ static bool build_mma_jobs_chunk(const ac::PaTables& t, ac::PaJobParams& jp, std
       for (int k = ka; k < ka + 4 * steps; ++k)
         mma_w4.push_back(k < kb ? t.band_w[t.band_ptr[i] + (k - t.band_k0[i])] : 0.f);
       job_desc.push_back(jb);
-      cost.push_back(13.5 * steps + (final ? 45.0 : 25.0));   // ~instructions per lane
+      cost.push_back(cm.step * steps + (final ? cm.final : cm.partial));   // ~instructions per lane
     }
     double total = 0, run = 0;
     for (double v : cost) total += v;
@@ -212,7 +221,7 @@ static bool build_mma_jobs_chunk(const ac::PaTables& t, ac::PaJobParams& jp, std
       for (int j = job_start[static_cast<size_t>(c) * 9 + ww]; j < job_start[static_cast<size_t>(c) * 9 + ww + 1]; ++j)
         load[ww] += cost[static_cast<size_t>(j) - first_job];
     const int rows = kc1 - kc0;
-    const double row_cost = 9.0;
+    const double row_cost = cm.ton_row;
     double lo = 0, hi = total + rows * row_cost;
     for (int it = 0; it < 60; ++it) {
       const double mid = 0.5 * (lo + hi);
