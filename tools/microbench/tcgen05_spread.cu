@@ -26,6 +26,20 @@
   } while (0)
 
 constexpr int kM = 64, kN = 64, kK = 64;
+#ifndef A_MN_MAJOR
+#define A_MN_MAJOR 0        // 1: the A operand as the masking kernel would write it - [band][item], items contiguous
+#endif
+#ifndef LD_16x256
+#define LD_16x256 0         // 1: read the accumulator in the mma.sync fragment layout (tcgen05.ld.16x256b)
+#endif
+#ifndef A_SBO
+#define A_SBO 144
+#endif
+#ifndef A_SWAP
+#define A_SWAP 0
+#endif
+constexpr int kASbo = A_SBO;            // MN-major A: bytes between cores of 4 items x 8 bands (128 B of data + 16 B pad:
+constexpr int kAKs = 16 * kASbo;      //   the lanes' 8-byte stores then fall on different banks), bytes per k-step
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -34,6 +48,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast
 __host__ __device__ inline int tile_offset_words(int mn, int k) {
   const int ks = k >> 3, kc = (k >> 2) & 1, e = k & 3, mc = mn >> 3, r = mn & 7;
   return ks * 512 + mc * 64 + kc * 32 + r * 4 + e;
+}
+
+// MN-major, no swizzle: core = 8 K-rows of 16 bytes (4 items); cores along M at kASbo
+__host__ __device__ inline int a_mn_offset_words(int m, int k) {
+  return ((k >> 3) * kAKs + (m >> 2) * kASbo + (k & 7) * 16 + (m & 3) * 4) / 4;
+}
+
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr >> 4) & 0x3fffu);
+  const uint32_t mn_stride = static_cast<uint32_t>(kASbo) >> 4, k_stride = static_cast<uint32_t>(kAKs) >> 4;
+  d |= static_cast<uint64_t>((A_SWAP ? mn_stride : k_stride) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((A_SWAP ? k_stride : mn_stride) & 0x3fffu) << 32;
+  d |= 1ull << 46;
+  return d;
 }
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -46,7 +75,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
 }
 
 // kind::tf32, fp32 accumulate, both operands K-major, M = 64, N = 64
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((kN >> 3) << 17) | ((kM >> 4) << 24);
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(A_MN_MAJOR) << 15) |
+                            ((kN >> 3) << 17) | ((kM >> 4) << 24);
 
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
   asm volatile(
@@ -62,8 +92,9 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
 __global__ void __launch_bounds__(128) spread_tcgen05_kernel(const float* __restrict__ p, const float* __restrict__ s,
                                                              float* __restrict__ out, long long* __restrict__ cycles,
                                                              int reps) {
-  extern __shared__ __align__(128) uint32_t dyn[];     // 4 operand tiles of 16 KB
-  uint32_t *a_hi = dyn, *a_lo = dyn + kM * kK, *b_hi = dyn + 2 * kM * kK, *b_lo = dyn + 3 * kM * kK;
+  extern __shared__ __align__(128) uint32_t dyn[];     // 4 operand tiles (A tiles padded in the MN-major variant)
+  constexpr int kATile = A_MN_MAJOR ? 8 * kAKs / 4 : kM * kK;
+  uint32_t *a_hi = dyn, *a_lo = dyn + kATile, *b_hi = dyn + 2 * kATile, *b_lo = dyn + 2 * kATile + kN * kK;
   __shared__ __align__(8) uint64_t mbar;
   __shared__ uint32_t tmem_base;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -73,8 +104,9 @@ __global__ void __launch_bounds__(128) spread_tcgen05_kernel(const float* __rest
     const int m = i / kK, k = i % kK;
     const float v = p[m * kK + k];
     const uint32_t hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
-    a_hi[tile_offset_words(m, k)] = hi;
-    a_lo[tile_offset_words(m, k)] = __float_as_uint(v - __uint_as_float(hi)) & 0xffffe000u;
+    const int ao = A_MN_MAJOR ? a_mn_offset_words(m, k) : tile_offset_words(m, k);
+    a_hi[ao] = hi;
+    a_lo[ao] = __float_as_uint(v - __uint_as_float(hi)) & 0xffffe000u;
     const float w = s[k * kN + m];                 // S[k][n = m]
     const uint32_t whi = (__float_as_uint(w) + 0x1000u) & 0xffffe000u;
     b_hi[tile_offset_words(m, k)] = whi;
@@ -102,10 +134,12 @@ __global__ void __launch_bounds__(128) spread_tcgen05_kernel(const float* __rest
       const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
 #pragma unroll
       for (int ks = 0; ks < kK / 8; ++ks) {
-        const uint32_t o = ks * 2048;
-        mma_tf32(tmem, make_desc(al + o), make_desc(bh + o), ks > 0 ? 1u : 0u);
-        mma_tf32(tmem, make_desc(ah + o), make_desc(bl + o), 1u);
-        mma_tf32(tmem, make_desc(ah + o), make_desc(bh + o), 1u);
+        const uint32_t o = ks * 2048, oa = A_MN_MAJOR ? ks * kAKs : o;
+        const uint64_t dal = A_MN_MAJOR ? make_desc_mn(al + oa) : make_desc(al + oa);
+        const uint64_t dah = A_MN_MAJOR ? make_desc_mn(ah + oa) : make_desc(ah + oa);
+        mma_tf32(tmem, dal, make_desc(bh + o), ks > 0 ? 1u : 0u);
+        mma_tf32(tmem, dah, make_desc(bl + o), 1u);
+        mma_tf32(tmem, dah, make_desc(bh + o), 1u);
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mbar))
                    : "memory");
@@ -129,6 +163,33 @@ __global__ void __launch_bounds__(128) spread_tcgen05_kernel(const float* __rest
     }
     parity ^= 1;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#if LD_16x256
+    // the mma.sync accumulator layout: thread (g = lane / 4, t = lane % 4) gets rows g, g + 8 and columns 2t, 2t + 1 of
+    // every block of 8 columns: v[4 i + 0 .. 3] = (g, 8i + 2t), (g, 8i + 2t + 1), (g + 8, 8i + 2t), (g + 8, 8i + 2t + 1)
+    uint32_t v[32];
+    const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x8.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, "
+        "%25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]),
+          "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+          "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (rep == reps - 1) {
+      const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        out[(warp * 16 + g) * kN + 8 * i + 2 * t] = __uint_as_float(v[4 * i]);
+        out[(warp * 16 + g) * kN + 8 * i + 2 * t + 1] = __uint_as_float(v[4 * i + 1]);
+        out[(warp * 16 + g + 8) * kN + 8 * i + 2 * t] = __uint_as_float(v[4 * i + 2]);
+        out[(warp * 16 + g + 8) * kN + 8 * i + 2 * t + 1] = __uint_as_float(v[4 * i + 3]);
+      }
+    }
+#else
     // M = 64: row m sits in lane (m % 16) + 32 (m / 16), i.e. lanes 0 .. 15 of warp m / 16; 64 fp32 columns per row
     uint32_t v[64];
     const uint32_t taddr = tmem + (static_cast<uint32_t>(warp * 32) << 16);
@@ -153,6 +214,7 @@ __global__ void __launch_bounds__(128) spread_tcgen05_kernel(const float* __rest
 #pragma unroll
       for (int n = 0; n < kN; ++n) out[m * kN + n] = __uint_as_float(v[n]);
     }
+#endif
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();                      // the accumulator has been read: the next product may overwrite it
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -187,7 +249,7 @@ int main() {
   CHECK(cudaMemcpy(dp, p.data(), p.size() * 4, cudaMemcpyHostToDevice));
   CHECK(cudaMemcpy(ds, s.data(), s.size() * 4, cudaMemcpyHostToDevice));
   CHECK(cudaMemset(dout, 0, out.size() * 4));
-  const int smem = 4 * kM * kK * 4;
+  const int smem = (A_MN_MAJOR ? 2 * 8 * kAKs : 2 * kM * kK * 4) + 2 * kN * kK * 4;
   CHECK(cudaFuncSetAttribute(spread_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   for (int reps : {1, 1000}) {
     spread_tcgen05_kernel<<<1, 128, smem>>>(dp, ds, dout, dcyc, reps);
@@ -210,9 +272,10 @@ int main() {
         worst = std::fmax(worst, std::fabs(out[m * kN + n] - ref) / ref);
         worst_fp32 = std::fmax(worst_fp32, std::fabs(ref32 - ref) / ref);
       }
-    std::printf("reps %d: %.1f cycles per 64 x 64 x 64 3xTF32 product (24 tcgen05.mma + commit + wait + tcgen05.ld of 64 columns); "
+    std::printf("A %s, accumulator read %s; reps %d: %.1f cycles per 64 x 64 x 64 3xTF32 product (24 tcgen05.mma + commit + wait + tcgen05.ld of 64 columns); "
                 "max relative error vs float64 %.3g (a sequential fp32 FMA sum: %.3g)\n",
-                reps, static_cast<double>(cyc) / reps, worst, worst_fp32);
+                A_MN_MAJOR ? "MN-major (items contiguous, 144 B cores)" : "K-major", LD_16x256 ? "16x256b.x8" : "32x32b.x64", reps,
+                static_cast<double>(cyc) / reps, worst, worst_fp32);
   }
   return 0;
 }
