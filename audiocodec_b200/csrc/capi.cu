@@ -1044,7 +1044,7 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
         tail.push_back(t);
         left -= t;
       }
-      if (!first) next *= 2;
+      if (!first && next < p->chunk_clips) next *= 2;    // saturates: a long batch runs this loop thousands of times
       first = false;
     }
     chunk_of = head;

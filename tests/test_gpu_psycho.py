@@ -416,3 +416,17 @@ def test_host_streaming_ring_is_bounded_and_reused():
   dev = torch.stack([big[i] for i in probe]).cuda()
   qd, sd = codec.encode(dev)
   assert torch.equal(out[probe], codec.decode(qd, sd).cpu())
+
+
+def test_host_streaming_long_schedule():
+  """More than 128 chunks: the ramp of the chunk schedule (1, 1, 2, 4, ... clips) must saturate at chunk_clips - it once
+  kept doubling into an int64 overflow, which produced empty chunks and an invalid launch configuration."""
+  sr, n, c = 44100, 256, 2
+  codec = audiocodec_b200.AudioCodec(sr, filters_n=n)
+  x = torch.from_numpy(oracle.synthetic_audio(150, 256 * 8, c, sr))
+  q, step = codec.encode(x.cuda())
+  ref = codec.decode(q, step).cpu()
+  for chunk in (1, 2):                                  # 150 / 76 chunks
+    assert torch.equal(codec.roundtrip_host(x.pin_memory(), chunk_clips=chunk), ref)
+  out, stats = codec.roundtrip_host(x.pin_memory(), chunk_clips=1, return_stats=True)
+  assert torch.equal(out, ref) and int(stats[0]) == q.numel() and int(stats[1]) == int((q != 0).sum())

@@ -37,7 +37,10 @@ lib = _capi.lib()
 lib.ac_debug_set_pa_trace.argtypes = [ctypes.c_void_p]
 assert lib.ac_debug_set_pa_trace(trace.data_ptr()) == 0
 torch.cuda.synchronize()
-pa.encode(y)
+if os.environ.get("TRACE_FUSED"):
+  codec.encode(x)          # the single-pass encoder: stamp 0 of a tile follows its bulk-copy wait and forward MDCT
+else:
+  pa.encode(y)
 torch.cuda.synchronize()
 np.save(os.path.join(ROOT, "gpurun_out", "k3_trace" + os.environ.get("TRACE_TAG", "") + ".npy"),
         trace.cpu().numpy().reshape(-1, 16, 4))
