@@ -71,6 +71,15 @@ cudaError_t upload(const std::vector<T>& host, const T** dev, std::vector<void*>
 
 namespace ac {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled(int kind) {
+  static const int mask = [] {
+    const char* e = std::getenv("AC_PDL");
+    // measured on cfg2 (tools/chain_probe.py): the masking kernel behind the forward MDCT gains 2.5 us per step, the
+    // forward MDCT behind the inverse nothing, the inverse MDCT behind the masking kernel LOSES 15 us - off by default
+    return e != nullptr ? std::atoi(e) : 3;
+  }();
+  return (mask & kind) != 0;
+}
 }  // namespace ac
 
 struct ac_mdct_plan {
@@ -198,7 +207,11 @@ static bool build_mma_jobs_chunk(const ac::PaTables& t, ac::PaJobParams& jp, std
       jb.z = steps;
       // byte offset of P[band][0] (64 items per band) with the XOR swizzle of the band folded in (the kernel xors
       // 8 * lane: a lane owns the item pair 2 lane, 2 lane + 1)
-      jb.w = (i * 256 + ((i & 3) << 5)) | (partial ? 0x10000 : 0) | (final ? 0x20000 : 0);
+      // bits 18 ..: the same row in the operand layout of the tcgen05 product (psycho_mma_kernels.cu, tc_desc): band i at
+      // position kp = i ^ 4, atoms of four bands 512 bytes apart, 128 bytes per band, 32-byte chunks XORed with kp & 3
+      const int kp = i ^ 4;
+      const int tc_off = (kp >> 2) * 512 + (kp & 3) * 128 + ((kp & 3) << 5);
+      jb.w = (i * 256 + ((i & 3) << 5)) | (partial ? 0x10000 : 0) | (final ? 0x20000 : 0) | (tc_off << 18);
       for (int k = ka; k < ka + 4 * steps; ++k)
         mma_w4.push_back(k < kb ? t.band_w[t.band_ptr[i] + (k - t.band_k0[i])] : 0.f);
       job_desc.push_back(jb);

@@ -191,6 +191,32 @@ cudaError_t dequantize_f64(const int32_t* q, const double* thr, double* y, int64
 void count_launch();
 int tile_sm_count();
 
+// Programmatic dependent launch (the tile kernels of the encode / decode chain): the launch carries the programmatic
+// stream-serialisation attribute, the kernel stages its tables, allocates tensor memory and initialises its barriers,
+// then executes griddepcontrol.wait before it touches a tensor - so its launch latency and prologue overlap the tail of
+// the kernel before it on the stream.  AC_PDL=0 launches without the attribute (A/B runs).
+// kind: 1 forward MDCT, 2 masking / single-pass encoder, 4 inverse MDCT (AC_PDL is a mask of the kinds that use it)
+bool pdl_enabled(int kind);
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t stream,
+                       Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled(kind) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 bool mdct_tile_forward_supported(int n, int channels);
 bool mdct_tile_inverse_supported(int n, int channels);
 cudaError_t mdct_forward_tile(const MdctDeviceTables& tb, const float* x, float* y, int64_t batches, int64_t blocks_n,

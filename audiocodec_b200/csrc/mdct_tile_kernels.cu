@@ -50,6 +50,8 @@ mdct_forward_tile_kernel(MdctDeviceTables tb, const float* __restrict__ x, float
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_launch_dependents();                  // the next kernel on the stream may start its prologue
+  pdl_wait();                               // the kernel before this one has completed: its tensors are visible
 
   // rows r in [r_lo, r_hi) of a tile hold real blocks, the others are the zero padding (mdctransformer.py:366)
   auto issue_load = [&](int64_t tile, int slot) {        // thread 0 only
@@ -154,6 +156,8 @@ mdct_inverse_dequant_tile_kernel(MdctDeviceTables tb, const int32_t* __restrict_
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_launch_dependents();                  // the next kernel on the stream may start its prologue
+  pdl_wait();                               // the kernel before this one has completed: its tensors are visible
 
   auto issue_load = [&](int64_t tile, float* dst, const void* src, uint64_t* bar) {        // thread 0 only
     const int64_t b = tile / tiles_per_row;
@@ -286,6 +290,8 @@ mdct_inverse_dequant_compact_tile_kernel(MdctDeviceTables tb, const int32_t* __r
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_launch_dependents();                  // the next kernel on the stream may start its prologue
+  pdl_wait();                               // the kernel before this one has completed: its tensors are visible
 
   auto issue_load = [&](int64_t tile, float* dst, const void* src, int row_floats, uint64_t* bar) {   // thread 0 only
     const int64_t b = tile / tiles_per_row;
@@ -420,7 +426,7 @@ cudaError_t launch_inverse_compact_tile(const MdctDeviceTables& tb, const int32_
   auto kernel = mdct_inverse_dequant_compact_tile_kernel<Plan, C, THREADS, kMinB>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmem));
   if (err != cudaSuccess) return err;
-  kernel<<<grid, THREADS, kSmem, stream>>>(tb, q, bark, filt4, eps_s2, x, frames_n, tiles_per_row, total);
+  err = launch_pdl(4, kernel, grid, THREADS, kSmem, stream, tb, q, bark, filt4, eps_s2, x, frames_n, tiles_per_row, total);
   count_launch();
   return cudaGetLastError();
 }
@@ -446,6 +452,8 @@ mdct_inverse_plain_tile_kernel(MdctDeviceTables tb, const float* __restrict__ y,
     mbar_fence_init();
   }
   __syncthreads();
+  pdl_launch_dependents();                  // the next kernel on the stream may start its prologue
+  pdl_wait();                               // the kernel before this one has completed: its tensors are visible
 
   auto issue_load = [&](int64_t tile, int slot) {        // thread 0 only
     const int64_t b = tile / tiles_per_row;
@@ -534,7 +542,7 @@ cudaError_t launch_forward_tile(const MdctDeviceTables& tb, const float* x, floa
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
   per_sm = std::max(1, std::min(per_sm, MINB));
   const int64_t cap = static_cast<int64_t>(tile_sm_count()) * per_sm;
-  kernel<<<static_cast<unsigned>(std::min(total, cap)), THREADS, smem, stream>>>(tb, x, y, blocks_n, tiles_per_row, total);
+  err = launch_pdl(1, kernel, static_cast<unsigned>(std::min(total, cap)), THREADS, smem, stream, tb, x, y, blocks_n, tiles_per_row, total);
   count_launch();
   return cudaGetLastError();
 }
@@ -561,12 +569,12 @@ cudaError_t launch_inverse_tile(const MdctDeviceTables& tb, const float* y, cons
     auto kernel = mdct_inverse_dequant_tile_kernel<Plan, C, THREADS, kMinB>;
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    kernel<<<grid, THREADS, smem, stream>>>(tb, q, thr, x, frames_n, tiles_per_row, total);
+    err = launch_pdl(4, kernel, grid, THREADS, smem, stream, tb, q, thr, x, frames_n, tiles_per_row, total);
   } else {
     auto kernel = mdct_inverse_plain_tile_kernel<Plan, C, THREADS, MINB>;
     err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     if (err != cudaSuccess) return err;
-    kernel<<<grid, THREADS, smem, stream>>>(tb, y, x, frames_n, tiles_per_row, total);
+    err = launch_pdl(4, kernel, grid, THREADS, smem, stream, tb, y, x, frames_n, tiles_per_row, total);
   }
   count_launch();
   return cudaGetLastError();

@@ -154,19 +154,29 @@ __device__ __forceinline__ void sts_b64(uint32_t addr, u64 v) {
 }
 
 struct Layout2 {
-  int powa, powia, t, tbuf, p, part, uv, sfh, sfl, quiet, lin, bw8, filt4, total;
+  int powa, powia, t, tbuf, p, part, uv, sfh, sfl, quiet, lin, bw8, filt4, misc, total;
 };
+
+// the exponent tables are only read by the table powers: plans on the split powers without the clamp do not stage them
+__host__ __device__ inline bool pow_tables_needed(const PaDeviceTables& tb) { return !tb.pow_split || tb.clamp_needed; }
+
+// TC (the spreading product on tcgen05.mma, see the kernel): both T chunk buffers and P start on 1024-byte boundaries
+// (P and - in the chunk buffer that is dead during the product - its low-order term are SWIZZLE_128B_BASE32B operand
+// tiles), the spreading function is staged as two tables of 30 K-major core matrices instead of two 128-entry tables
+constexpr int kTcCores = 30, kTcTable = kTcCores * 32;
+constexpr int kTcIssuer = 64;         // the thread that issues the product: lane 0 of a warp without per-item constants to compute
 
 // fused: the single-pass encoder (x -> q): T holds ALL filters of the tile's frames (the forward MDCT leaves them
 // there, transposed) instead of two chunk buffers
-__host__ __device__ inline Layout2 layout2(const PaDeviceTables& tb, const bool fused = false) {
+__host__ __device__ inline Layout2 layout2(const PaDeviceTables& tb, const bool fused = false, const bool tc = false) {
   Layout2 L;
   const int kc = tb.n < tb.mma_chunk_k ? tb.n : tb.mma_chunk_k;
   const int t_rows = ((fused ? tb.n : kc) + 3) * kTS;   // 3 zero rows behind the chunk for the 4-filter steps
   int o = 0;
-  L.powa = o;    o += 512;                              // the exponent tables come first: an index with the sign bit
-  L.powia = o;   o += 512;                              //   set (NaN input) still reads inside the allocation
-  L.tbuf = (t_rows + 3) & ~3;
+  const int pow_words = pow_tables_needed(tb) ? 512 : 0;
+  L.powa = o;    o += pow_words;                        // the exponent tables come first: an index with the sign bit
+  L.powia = o;   o += pow_words;                        //   set (NaN input) still reads inside the allocation
+  L.tbuf = tc ? (t_rows + 255) & ~255 : (t_rows + 3) & ~3;
   L.t = o;       o += (fused ? 1 : 2) * L.tbuf;         // two chunk buffers: one is filled while the other is read
   // G [64][kGS] aliases P and the tonality partials behind it: both are dead once the MMA loop and the per-item
   // constants are done, and are next written behind the first barrier of the next tile
@@ -174,14 +184,22 @@ __host__ __device__ inline Layout2 layout2(const PaDeviceTables& tb, const bool 
   L.p = o;       o += kNB * kPS;
   L.part = o;    o += 2 * kWarps * kTI;
   L.uv = o;      o += 3 * kTI;
-  L.sfh = o;     o += 128;
-  L.sfl = o;     o += 128;
+  L.sfh = o;     o += tc ? kTcTable : 128;
+  L.sfl = o;     o += tc ? kTcTable : 128;
   L.quiet = o;   o += kNB;
   L.lin = o;     o += kNB;
   L.bw8 = o;     o += (2 * tb.n_mma_w4 + 3) & ~3;        // every weight twice: a packed pair for both items of a lane
   L.filt4 = o;   o += filt_in_smem(tb) ? 4 * tb.n : 0;   // long filter tables stay in global memory (L1 / L2)
+  // mbarrier of the tcgen05 product (8 bytes), tensor-memory address, mbarrier of the fused encoder's bulk copy, the two
+  // ticket slots of the tile scheduler: no static shared memory, so the dynamic window starts 1024-byte aligned
+  L.misc = o;    o += 12;
   L.total = o;
   return L;
+}
+
+// the tensor-memory port needs a dead chunk buffer that holds the 16 KB low-order term of P
+__host__ __device__ inline bool tc_layout_ok(const PaDeviceTables& tb) {
+  return layout2(tb, false, true).tbuf >= kNB * kTI && tb.mma_n_chunks >= 2;
 }
 
 // asynchronous global -> shared copies of 4 or 8 bytes (LDGSTS): the destination address is free, so the copy
@@ -485,6 +503,71 @@ __device__ __forceinline__ void phase_d_unit_pairs(const float4* __restrict__ fi
   }
 }
 
+// ---- tcgen05 (5th-generation tensor cores): the spreading product of a tile as 24 single-thread instructions ----------
+// acc[item][j] = sum_i P[item][i] S[i][j] is M = 64 items x N = 64 bands x K = 64 bands: eight k-steps of
+// tcgen05.mma.cta_group::1.kind::tf32 (M = 64, N = 64, K = 8), three instructions per k-step for the error-compensated
+// product (P_lo S_hi + P_hi S_lo + P_hi S_hi), accumulator in 64 columns of tensor memory.  Operands
+// (tools/microbench/tcgen05_toeplitz.cu measured both forms on a B200: 6.6e-7 / 1.1e-6 against float64):
+//   A = P, MN-major (items contiguous, as the band-sum phase stores it), SWIZZLE_128B_BASE32B: band position kp, item i at
+//       byte (i >> 5) 8192 + (kp >> 2) 512 + (kp & 3) 128 + (((i & 31) 4) ^ ((kp & 3) << 5)); descriptor: leading byte
+//       offset 8192 (the next 32 items), stride byte offset 512 (the next four bands).  P_hi is P as stored (the tensor
+//       core ignores the low 13 mantissa bits), P_lo = P - trunc(P) is written to the chunk buffer that is dead during the
+//       product.
+//   B = S, K-major, no swizzle.  S is Toeplitz (S[i][j] = f[64 - i + j]): the core matrix (8 n-rows x 4 k) of column
+//       block nb and k-block kb only depends on c = 2 nb - kb, so the 128 cores of the dense operand are 30 distinct ones,
+//       and because a descriptor addresses cores affinely (start + nb SBO + kb LBO) a 3840-byte table serves: with the
+//       two K-cores of a k-step in DESCENDING band order (band i sits at position kp = i ^ 4 of A) c grows with both
+//       steps: LBO = 128 B, SBO = 256 B, start = table + (14 - 2 ks) 128.  Core c, row r, element e = f[4 + 4 c + r - e].
+// The accumulator comes back with tcgen05.ld.16x256b in the mma.sync fragment layout (thread (g, t): rows g, g + 8,
+// columns 2t, 2t + 1 of every 8-column block), so the epilogue is the one of the mma.sync path.
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return static_cast<uint64_t>((saddr >> 4) & 0x3fffu) | (static_cast<uint64_t>((lbo >> 4) & 0x3fffu) << 16) |
+         (static_cast<uint64_t>((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46) | (static_cast<uint64_t>(layout & 7u) << 61);
+}
+// kind::tf32 (a / b format 2), fp32 accumulate (c format 1), A MN-major (bit 15), B K-major, N = 64 (>> 3), M = 64 (>> 4)
+constexpr uint32_t kTcIdesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((kNB >> 3) << 17) | ((kTI >> 4) << 24);
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(kTcIdesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_mbar(uint32_t mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred q;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n"
+      "@!q bra WAIT_%=;\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+// 16 rows x 32 columns of the accumulator: v[4 i + e] = mma.sync element e of n-tile i
+__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, float (&acc)[4][4]) {
+  uint32_t v[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[i][e] = __uint_as_float(v[4 * i + e]);
+}
+
 #ifdef AC_PA_TRACE
 // development build only (tools/k3_trace.py): per CTA and tile, the global timer at the start of the chunk loop, of the
 // MMA phase, of phase D and at the end of phase D; slot 0 of a CTA holds its SM id
@@ -507,7 +590,7 @@ __device__ __forceinline__ void pa_trace(int slot, int ev) {
 // amplitudes TRANSPOSED into the same region (T[filter][item], all filters resident) once every group has finished its
 // FFT exchanges - Y never goes to global memory.  The phases below then read T exactly like a chunk buffer, phase D
 // takes its amplitudes from T instead of L2, and the next tile's blocks are requested when phase D is done.
-template <int C, bool QUANT, int NFIX, int MINB, bool FUSED = false>
+template <int C, bool QUANT, int NFIX, int MINB, bool FUSED = false, bool TC = false>
 __global__ void __launch_bounds__(kThreads, MINB)
 pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_constant__ PaJobParams jp,
                    const float* __restrict__ y, const float* __restrict__ ton_in, float one_minus_drown, float thr_scale,
@@ -521,8 +604,8 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   constexpr int ROWS = FT / kWarps;             // frame rows per warp
   static_assert(FT % kWarps == 0, "tile shape");
   static_assert(!FUSED || (C == 2 && NFIX == 256), "the fused encoder is built for stereo, filters_n = 256");
-  extern __shared__ __align__(128) float sm[];
-  const Layout2 L = layout2(tb, FUSED);
+  extern __shared__ __align__(1024) float sm[];  // TC: P and the chunk buffers are swizzled operand tiles (1024-byte atoms)
+  const Layout2 L = layout2(tb, FUSED, TC);
   const int n = NFIX > 0 ? NFIX : tb.n, kc = n < tb.mma_chunk_k ? n : tb.mma_chunk_k;
   const int n_chunks = tb.mma_n_chunks;
   float2* s_powa = reinterpret_cast<float2*>(sm + L.powa);
@@ -548,8 +631,18 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     // the tables: every global load of a thread is issued before its first shared-memory store (one round trip to L2
     // instead of one per table); kThreads == 256 == entries of the exponent tables
     static_assert(kThreads == 256, "one exponent-table entry per thread");
-    const float2 pa = tb.pow_alpha[tid], pia = tb.pow_inv_alpha[tid];
+    const bool pow_tabs = pow_tables_needed(tb);
+    const float2 pa = pow_tabs ? tb.pow_alpha[tid] : make_float2(0.f, 0.f);
+    const float2 pia = pow_tabs ? tb.pow_inv_alpha[tid] : make_float2(0.f, 0.f);
     const float sfv = tb.spread_fn[tid & 127];
+    float zv[4];                                // TC: this thread's entries of the Toeplitz core table (see tc_desc)
+    if constexpr (TC) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = tid + u * kThreads;
+        zv[u] = i < kTcTable ? tb.spread_fn[4 + 4 * (i >> 5) + ((i >> 2) & 7) - (i & 3)] : 0.f;
+      }
+    }
     const float qv = tb.quiet[tid & (kNB - 1)], lv = tb.lin[tid & (kNB - 1)];
     const int nw = tb.n_mma_w4;
     float wv[4];
@@ -559,9 +652,22 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
 #pragma unroll
     for (int u = 0; u < 2; ++u)
       fv[u] = filt_smem && tid + u * kThreads < n ? tb.filt4[tid + u * kThreads] : make_float4(0.f, 0.f, 0.f, 0.f);
-    s_powa[tid] = pa;
-    s_powia[tid] = pia;
-    if (tid < 128) {
+    if (pow_tabs) {
+      s_powa[tid] = pa;
+      s_powia[tid] = pia;
+    }
+    if constexpr (TC) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = tid + u * kThreads;
+        if (i < kTcTable) {
+          uint32_t hi, lo;
+          split_tf32(zv[u], hi, lo);
+          s_sfh[i] = hi;
+          s_sfl[i] = lo;
+        }
+      }
+    } else if (tid < 128) {
       uint32_t hi, lo;
       split_tf32(sfv, hi, lo);
       s_sfh[tid] = hi;
@@ -597,18 +703,37 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     for (int i = tid; i < 2 * 3 * TS; i += kThreads)
       sm[L.t + (i / (3 * TS)) * L.tbuf + kc * TS + (i % (3 * TS))] = 0.f;
   }
-  __shared__ __align__(8) uint64_t s_mbar;     // FUSED: completion of the tile's bulk copy
+  uint64_t& s_mbar = *reinterpret_cast<uint64_t*>(sm + L.misc + 4);     // FUSED: completion of the tile's bulk copy
   if (FUSED && tid == 0) {
     mbar_init(&s_mbar, 1);
     mbar_fence_init();
   }
   if constexpr (FUSED) __syncthreads();
+  // TC: 64 columns of tensor memory for the accumulator of the spreading product (three CTAs per SM: 192 of 512), the
+  // mbarrier its completion arrives on
+  uint32_t tc_tmem = 0, tc_parity = 0;
+  const uint32_t tc_mbar = static_cast<uint32_t>(__cvta_generic_to_shared(sm + L.misc));
+  if constexpr (TC) {
+    if (tid == 0) {
+      mbar_init(reinterpret_cast<uint64_t*>(sm + L.misc), 1);
+      mbar_fence_init();
+    }
+    if (warp == 0) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;" ::"r"(tc_mbar + 8u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    tc_tmem = *reinterpret_cast<volatile uint32_t*>(sm + L.misc + 2);
+  }
 
   const uint32_t sm_base = static_cast<uint32_t>(__cvta_generic_to_shared(sm));
   const uint32_t t_base = sm_base + static_cast<uint32_t>(L.t) * 4u;
   const uint32_t tbuf_bytes = static_cast<uint32_t>(L.tbuf) * 4u;
   const uint32_t w_base = sm_base + static_cast<uint32_t>(L.bw8) * 4u;
   const uint32_t p_base = sm_base + static_cast<uint32_t>(L.p) * 4u;
+  const uint32_t tc_lane_off = ((static_cast<uint32_t>(lane) & 15u) << 3) | ((static_cast<uint32_t>(lane) >> 4) << 13);
   const float eps = tb.eps;
   const bool pow_split = tb.pow_split != 0;
   const float eps_s2 = eps * scale2;
@@ -678,7 +803,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   // finishes.  A ticket is drawn at the start of a tile and published through shared memory before the barrier of the
   // tile's last chunk, behind which the first chunk of the next tile is requested.  The last CTA to finish
   // (sched[1]) re-arms both counters for the next launch.
-  __shared__ long long s_next[2];
+  volatile long long* s_next = reinterpret_cast<volatile long long*>(sm + L.misc + 8);
   int par = 0;                                  // buffer of the chunk that is processed next
   int tpar = 0;                                 // parity of the tile (slot of s_next)
   int64_t tile_i = blockIdx.x;
@@ -702,6 +827,8 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       }
     }
   };
+  pdl_launch_dependents();                      // the next kernel on the stream may start its prologue
+  pdl_wait();                                   // the producer of y (x) has completed; the tables above are plan constants
   if (tile_i < tiles) {
     if constexpr (FUSED) {
       if (tid == 0) issue_x_load(tile_i);
@@ -886,7 +1013,9 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
             a1 = ffma2(fmul2(y3, y3), w3, a1);
           }
           u64 acc2 = fadd2(a0, a1);
-          const uint32_t pp = p_base + ((static_cast<uint32_t>(jb.w) & 0xffffu) ^ (static_cast<uint32_t>(lane) << 3));
+          // TC: the operand layout of tc_desc (bits 18.. of the descriptor word; lanes 16 - 31 own items 32 - 63)
+          const uint32_t pp = TC ? p_base + ((static_cast<uint32_t>(jb.w) >> 18) ^ tc_lane_off)
+                                 : p_base + ((static_cast<uint32_t>(jb.w) & 0xffffu) ^ (static_cast<uint32_t>(lane) << 3));
           if (jb.w & 0x10000) acc2 = fadd2(acc2, lds_b64<0>(pp));
           if (jb.w & 0x20000) {
             float ax, ay;
@@ -912,8 +1041,58 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       *reinterpret_cast<u64*>(s_part + warp * TI + 2 * lane) = ton_i2;
       *reinterpret_cast<u64*>(s_part + (kWarps + warp) * TI + 2 * lane) = ton_l2;
     }
+    // The product is issued as two groups on the same accumulator: P_hi (S_lo + S_hi) over all k-steps right behind the
+    // barrier that completes P, then P_lo S_hi.  P as it stands is P_hi (the tensor core ignores the low 13 mantissa bits);
+    // P_lo = P - trunc(P) is made while the first group runs and goes
+    //   chain kernel: into the chunk buffer that is dead until the next tile's second chunk is requested (`par` is the
+    //     buffer the next tile's first chunk is landing in);
+    //   single-pass encoder (no dead buffer, T holds the amplitudes): over P itself once the first group has read it.
+    // The instruction order is the same, so both kernels produce the same bits.
+    constexpr bool INPLACE = FUSED;
+    const uint32_t lo_base = INPLACE ? p_base : t_base + static_cast<uint32_t>(par ^ 1) * tbuf_bytes;
+    auto split_lo = [&](float4* l4) {
+      const float4* p4 = reinterpret_cast<const float4*>(P);
+#pragma unroll
+      for (int u = 0; u < kNB * kTI / 4 / kThreads; ++u) {
+        const float4 v = p4[tid + u * kThreads];
+        float4 r;
+        r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        l4[tid + u * kThreads] = r;
+      }
+    };
+    // descriptors of k-step 0; a k-step moves the start address (16-byte units in the low word) by +1024 bytes in P and
+    // by -256 bytes in the core table - the issuing thread spends an add per operand, not a descriptor build
+    const uint32_t zh = sm_base + static_cast<uint32_t>(L.sfh) * 4u, zl = sm_base + static_cast<uint32_t>(L.sfl) * 4u;
+    const uint64_t d_phi = tc_desc(p_base, 8192, 512, 1), d_plo = tc_desc(lo_base, 8192, 512, 1);
+    const uint64_t d_zh = tc_desc(zh + 14 * 128, 128, 256, 0), d_zl = tc_desc(zl + 14 * 128, 128, 256, 0);
+    auto issue_hi = [&]() {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        tc_mma_tf32(tc_tmem, d_phi + static_cast<uint64_t>(ks * 64), d_zl - static_cast<uint64_t>(ks * 16), ks > 0 ? 1u : 0u);
+        tc_mma_tf32(tc_tmem, d_phi + static_cast<uint64_t>(ks * 64), d_zh - static_cast<uint64_t>(ks * 16), 1u);
+      }
+    };
+    auto issue_lo = [&]() {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks)
+        tc_mma_tf32(tc_tmem, d_plo + static_cast<uint64_t>(ks * 64), d_zh - static_cast<uint64_t>(ks * 16), 1u);
+    };
+    if constexpr (TC) {
+      fence_async_smem();                       // this thread's stores of P (the band sums) -> async proxy
+      tc_fence_before();                        // its reads of the previous tile's accumulator are over
+    }
     __syncthreads();                            // P and the tonality partials are complete
     PA_TRACE(slot_i, 1);
+    if constexpr (TC) {                         // the first group runs while the low-order term / the constants are made
+      if (tid == kTcIssuer && !(ablate & 4)) {
+        tc_fence_after();
+        issue_hi();
+        if constexpr (INPLACE) tc_commit(tc_mbar);
+      }
+    }
 
     // ---- per-item constants of the masking offset (psychoacoustic.py:185-191), once per tile
     if (warp < TI / 32) {
@@ -950,6 +1129,30 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+      if constexpr (TC) {
+        if constexpr (INPLACE) {
+          if (!(ablate & 4)) {
+            tc_wait_mbar(tc_mbar, tc_parity);   // the first group has read P
+            tc_parity ^= 1u;
+          }
+          split_lo(reinterpret_cast<float4*>(P));
+        } else {
+          split_lo(reinterpret_cast<float4*>(sm + L.t + (par ^ 1) * L.tbuf));
+        }
+        fence_async_smem();                     // this thread's part of the low-order term -> async proxy
+        __syncthreads();                        // the low-order term is complete; the per-item constants are visible
+        if (!(ablate & 4)) {
+          if (tid == kTcIssuer) {
+            tc_fence_after();
+            issue_lo();
+            tc_commit(tc_mbar);
+          }
+          tc_wait_mbar(tc_mbar, tc_parity);
+          tc_parity ^= 1u;
+          tc_fence_after();
+          tc_ld_16x256b_x4(tc_tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(32 * nq), acc);
+        }
+      } else {
       uint32_t bh0[4], bh1[4], bl0[4], bl1[4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
@@ -989,6 +1192,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       }
 
       __syncthreads();                          // the per-item constants are visible; P is free
+      }
       // masking offset, non-linear superposition, quiet threshold            (psychoacoustic.py:185-208, :144)
       const int ma = m0 + g, mb = m0 + g + 8;
       if (ablate & 8) {
@@ -1225,6 +1429,11 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     sched[0] = 0u;
     sched[1] = 0u;
   }
+  if constexpr (TC) {
+    tc_fence_before();
+    __syncthreads();                            // every warp has read its last accumulator
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;" ::"r"(tc_tmem) : "memory");
+  }
 #ifdef AC_PA_TRACE
   if (threadIdx.x == 0 && g_pa_trace != nullptr) {
     unsigned smid;
@@ -1265,11 +1474,11 @@ int mma_sm_count() {
   return cached;
 }
 
-template <int C, bool QUANT, int NFIX, int MINB>
+template <int C, bool QUANT, int NFIX, int MINB, bool TC>
 cudaError_t launch_mma_tile_nb(const PaDeviceTables& tb, const float* y, const float* ton_in, float omd, float thr_scale,
                                float* thr_out, int32_t* q_out, int64_t frames, int per_sm, cudaStream_t stream) {
   constexpr int FT = kTI / C;
-  const size_t smem = static_cast<size_t>(layout2(tb).total) * sizeof(float);
+  const size_t smem = static_cast<size_t>(layout2(tb, false, TC).total) * sizeof(float);
   const int64_t tiles = (frames + FT - 1) / FT;
   const int64_t cap = static_cast<int64_t>(mma_sm_count()) * per_sm;
   const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
@@ -1277,13 +1486,13 @@ cudaError_t launch_mma_tile_nb(const PaDeviceTables& tb, const float* y, const f
   // experiments (profiles/README.md, ablation table): bit 0 skips the tonality pass, 1 the band sums, 2 the MMA loop,
   // 3 its epilogue, 4 phase D, 5 the asynchronous copies of y - the results are then wrong, only the time is of interest
   if (const char* e = std::getenv("AC_PA_ABLATE")) ablate = std::atoi(e);
-  auto kernel = pa_mma_tile_kernel<C, QUANT, NFIX, MINB>;
+  auto kernel = pa_mma_tile_kernel<C, QUANT, NFIX, MINB, false, TC>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
-  kernel<<<grid, kThreads, smem, stream>>>(tb, *tb.jobs_host, y, ton_in, omd, thr_scale, thr_out, q_out, frames, tiles,
-                                           pa_sched_slot(tb), ablate, MdctDeviceTables{}, 0, 0);
+  err = launch_pdl(2, kernel, grid, kThreads, smem, stream, tb, *tb.jobs_host, y, ton_in, omd, thr_scale, thr_out, q_out, frames,
+                   tiles, pa_sched_slot(tb), ablate, MdctDeviceTables{}, 0, 0);
   count_launch();
-  return cudaGetLastError();
+  return err != cudaSuccess ? err : cudaGetLastError();
 }
 
 // CTAs per SM: four when the shared memory of the plan allows it (32-filter chunks; the kernel is then compiled for 64
@@ -1291,13 +1500,26 @@ cudaError_t launch_mma_tile_nb(const PaDeviceTables& tb, const float* y, const f
 template <int C, bool QUANT, int NFIX>
 cudaError_t launch_mma_tile_n(const PaDeviceTables& tb, const float* y, const float* ton_in, float omd, float thr_scale,
                               float* thr_out, int32_t* q_out, int64_t frames, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(layout2(tb).total) * sizeof(float);
-  int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
-  per_sm = per_sm > 4 ? 4 : (per_sm < 1 ? 1 : per_sm);
+  auto ctas_per_sm = [](size_t smem) {
+    const int v = static_cast<int>((227 * 1024) / (smem + 1024));
+    return v > 4 ? 4 : (v < 1 ? 1 : v);
+  };
+  int per_sm = ctas_per_sm(static_cast<size_t>(layout2(tb).total) * sizeof(float));
+  // the spreading product on tcgen05 (tensor memory) when its operand layout costs no resident CTA; AC_PA_MMA=sync keeps
+  // the mma.sync product (A/B runs, cross-check tests)
+  bool tc = false;
+  if (tc_layout_ok(tb)) {
+    const int per_sm_tc = ctas_per_sm(static_cast<size_t>(layout2(tb, false, true).total) * sizeof(float));
+    const char* e = std::getenv("AC_PA_MMA");
+    tc = per_sm_tc >= (per_sm > 3 ? 3 : per_sm) && !(e != nullptr && e[0] == 's');
+    if (tc) per_sm = per_sm_tc > 3 ? 3 : per_sm_tc;
+  }
   if (const char* e = std::getenv("AC_PA_CTAS")) per_sm = std::max(1, std::min(per_sm, std::atoi(e)));   // experiments
+  if (tc)
+    return launch_mma_tile_nb<C, QUANT, NFIX, 3, true>(tb, y, ton_in, omd, thr_scale, thr_out, q_out, frames, per_sm, stream);
   if (per_sm >= 4)
-    return launch_mma_tile_nb<C, QUANT, NFIX, 4>(tb, y, ton_in, omd, thr_scale, thr_out, q_out, frames, per_sm, stream);
-  return launch_mma_tile_nb<C, QUANT, NFIX, 3>(tb, y, ton_in, omd, thr_scale, thr_out, q_out, frames, per_sm, stream);
+    return launch_mma_tile_nb<C, QUANT, NFIX, 4, false>(tb, y, ton_in, omd, thr_scale, thr_out, q_out, frames, per_sm, stream);
+  return launch_mma_tile_nb<C, QUANT, NFIX, 3, false>(tb, y, ton_in, omd, thr_scale, thr_out, q_out, frames, per_sm, stream);
 }
 
 // filters_n of the headline configurations are compile-time values (row strides become immediates)
@@ -1389,7 +1611,7 @@ cudaError_t pa_expand_threshold(const PaDeviceTables& tb, const float* bark, flo
 // ---- the single-pass encoder: x -> (q, step | bark thresholds) without the amplitudes in global memory ------------
 bool pa_encode_fused_supported(const PaDeviceTables& tb, const MdctDeviceTables& mt, int channels) {
   return channels == 2 && tb.n == 256 && mt.n == 256 && mt.pre_fwd != nullptr && pa_mma_tile_supported(tb, channels) &&
-         static_cast<size_t>(layout2(tb, true).total) * sizeof(float) <= 113 * 1024;
+         static_cast<size_t>(layout2(tb, true, true).total) * sizeof(float) <= 112 * 1024;
 }
 
 cudaError_t pa_encode_fused(const PaDeviceTables& tb_in, const MdctDeviceTables& mt, const float* x, float drown,
@@ -1405,19 +1627,22 @@ cudaError_t pa_encode_fused(const PaDeviceTables& tb_in, const MdctDeviceTables&
   const int64_t frames = blocks_n + 1;
   const int tiles_per_row = static_cast<int>((frames + FT - 1) / FT);
   const int64_t tiles = batches * tiles_per_row;
-  const size_t smem = static_cast<size_t>(layout2(tb, true).total) * sizeof(float);
+  // the same spreading product as the chain kernel (tcgen05, or mma.sync under AC_PA_MMA=sync): the two stay bit-identical
+  const char* e = std::getenv("AC_PA_MMA");
+  const bool tc = !(e != nullptr && e[0] == 's');
+  const size_t smem = static_cast<size_t>(layout2(tb, true, tc).total) * sizeof(float);
   int per_sm = static_cast<int>((227 * 1024) / (smem + 1024));
   per_sm = per_sm > 2 ? 2 : (per_sm < 1 ? 1 : per_sm);
   const int64_t cap = static_cast<int64_t>(mma_sm_count()) * per_sm;
   const unsigned grid = static_cast<unsigned>(tiles < cap ? tiles : cap);
-  auto kernel = pa_mma_tile_kernel<C, true, 256, 2, true>;
+  auto kernel = tc ? pa_mma_tile_kernel<C, true, 256, 2, true, true> : pa_mma_tile_kernel<C, true, 256, 2, true, false>;
   cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (err != cudaSuccess) return err;
-  kernel<<<grid, kThreads, smem, stream>>>(tb, *tb.jobs_host, x, nullptr, static_cast<float>(1.0 - static_cast<double>(drown)),
-                                           thr_scale, thr_out, q_out, batches * frames, tiles, pa_sched_slot(tb), 0, mt,
-                                           static_cast<int>(blocks_n), tiles_per_row);
+  err = launch_pdl(2, kernel, grid, kThreads, smem, stream, tb, *tb.jobs_host, x, nullptr,
+                   static_cast<float>(1.0 - static_cast<double>(drown)), thr_scale, thr_out, q_out, batches * frames, tiles,
+                   pa_sched_slot(tb), 0, mt, static_cast<int>(blocks_n), tiles_per_row);
   count_launch();
-  return cudaGetLastError();
+  return err != cudaSuccess ? err : cudaGetLastError();
 }
 
 bool pa_mma_tile_supported(const PaDeviceTables& tb, int channels) {

@@ -250,7 +250,13 @@ def test_mma_tile_kernel_against_other_kernels(sr, n, c, b, m, monkeypatch):
     out[kernel] = (q.cpu().numpy(), step.cpu().numpy(), thr.cpu().numpy())
     assert torch.equal(q, pa.quantize(y, step))             # the fused division is the IEEE one
   monkeypatch.delenv("AC_PA_KERNEL")
-  for other in ("fma", "generic"):
+  # the spreading product on tcgen05 / tensor memory (the default where its operand tiles fit) against mma.sync
+  monkeypatch.setenv("AC_PA_MMA", "sync")
+  q, step = pa.encode(y, thr_scale=1.5, drown=0.25)
+  thr = pa.global_masking_threshold(y, pa.tonality(y), drown=0.25)
+  out["sync"] = (q.cpu().numpy(), step.cpu().numpy(), thr.cpu().numpy())
+  monkeypatch.delenv("AC_PA_MMA")
+  for other in ("fma", "generic", "sync"):
     np.testing.assert_allclose(out["mma"][1], out[other][1], rtol=5e-6)
     np.testing.assert_allclose(out["mma"][2], out[other][2], rtol=5e-6)
     diff = np.abs(out["mma"][0].astype(np.int64) - out[other][0])
@@ -281,6 +287,14 @@ def test_full_size_encode_cfg2_kernels_agree(monkeypatch):
   assert rel <= 5e-6
   dq = (q - q_fma).abs()
   assert dq.max().item() <= 1 and (dq != 0).float().mean().item() <= 1e-3
+  del q_fma, step_fma, dq
+  monkeypatch.setenv("AC_PA_MMA", "sync")                   # mma.sync product against the tcgen05 product (the default)
+  q_sync, step_sync = pa.encode(y)
+  monkeypatch.delenv("AC_PA_MMA")
+  assert ((step - step_sync).abs() / step_sync).max().item() <= 5e-6
+  dq = (q - q_sync).abs()
+  assert dq.max().item() <= 1 and (dq != 0).float().mean().item() <= 1e-3
+  del q_sync, step_sync, dq
   # decode: the reconstruction error of every coefficient is at most half a quantiser step (+ fp32 rounding of y / step
   # and q * step)
   err = (pa.dequantize(q, step) - y).abs()

@@ -168,6 +168,8 @@ def test_mma_job_list_reproduces_w(sr, n):
       x, y, steps, wd = (int(v) for v in jobs[4 * j:4 * j + 4])
       band, swz = (wd & 0xffff) // 256, ((wd & 0xffff) % 256) // 4
       assert swz == (band & 3) << 3 and x % 264 == 0 and y % 32 == 0 and steps >= 1
+      kp = band ^ 4                                            # the same row in the tcgen05 operand layout (bits 18 ..)
+      assert (wd >> 18) == (kp >> 2) * 512 + (kp & 3) * 128 + ((kp & 3) << 5) and wd > 0
       row0 = x // 264
       assert row0 + 4 * steps <= kcn + 3                       # padded steps stay inside the three zero rows
       assert bool(wd & 0x10000) == (band in seen_band)         # an earlier chunk holds the first part of the band

@@ -71,11 +71,11 @@ for label, env in [("full", {}), ("ablate all (63)", {"AC_PA_ABLATE": "63"}), ("
                    ("skip A (3+32)", {"AC_PA_ABLATE": "35"}), ("skip B (12)", {"AC_PA_ABLATE": "12"}), ("skip D (16)", {"AC_PA_ABLATE": "16"}),
                    ("skip A,B (47)", {"AC_PA_ABLATE": "47"})] + [(k, dict(kv.split("=") for kv in v.split(","))) for k, v in
                                                                   (e.split(":") for e in os.environ.get("PROBE_EXTRA", "").split(";") if e)]:
-  for k in ("AC_PA_ABLATE", "AC_PA_CTAS"):
+  for k in ("AC_PA_ABLATE", "AC_PA_CTAS", "AC_PA_MMA"):
     os.environ.pop(k, None)
   os.environ.update(env)
   print(f"K3 {label:24s}: back to back {back_to_back(k3):7.2f} us, per launch {per_launch(k3):7.2f} us")
-for k in ("AC_PA_ABLATE", "AC_PA_CTAS"):
+for k in ("AC_PA_ABLATE", "AC_PA_CTAS", "AC_PA_MMA"):
   os.environ.pop(k, None)
 print(f"K1: back to back {back_to_back(k1):.2f} us, per launch {per_launch(k1):.2f} us")
 print(f"K2: back to back {back_to_back(k2):.2f} us, per launch {per_launch(k2):.2f} us")
