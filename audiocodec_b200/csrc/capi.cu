@@ -162,19 +162,12 @@ int unwrap_dl(struct DLManagedTensor* m, const char* name, int ndim, uint8_t cod
 static bool build_mma_jobs_chunk(const ac::PaTables& t, ac::PaJobParams& jp, std::vector<float>& mma_w4, int* chunk_k,
                                  int* n_chunks_out, int* n_jobs_out, int mma_chunk_k);
 
-// filters per chunk of the masking kernel's double-buffered tile: 64 (three CTAs per SM).  32-filter chunks leave room
-// for four CTAs per SM but measured slower on B200 (0.189 against 0.171 ms on cfg2, profiles/README.md);
-// AC_PA_CHUNK=32|64 forces one (experiments; read when a plan is created).
+// filters per chunk of the masking kernel's double-buffered tile: 64, a compile-time constant of the kernel (kChunk in
+// psycho_mma_kernels.cu; 32-filter chunks with four CTAs per SM measured slower on B200, profiles/README.md)
 static bool build_mma_jobs(const ac::PaTables& t, ac::PaJobParams& jp, std::vector<float>& mma_w4, int* chunk_k,
                            int* n_chunks_out, int* n_jobs_out) {
-  int forced = 0;
-  if (const char* e = std::getenv("AC_PA_CHUNK")) forced = std::atoi(e);
-  for (int ck : {64, 32}) {
-    if ((forced == 32 || forced == 64) && ck != forced) continue;
-    mma_w4.clear();
-    if (build_mma_jobs_chunk(t, jp, mma_w4, chunk_k, n_chunks_out, n_jobs_out, ck)) return true;
-  }
-  return false;
+  mma_w4.clear();
+  return build_mma_jobs_chunk(t, jp, mma_w4, chunk_k, n_chunks_out, n_jobs_out, 64);
 }
 
 // instructions per lane of a step of four filters, of the tail of a job that completes / does not complete its band, and
@@ -205,13 +198,14 @@ static bool build_mma_jobs_chunk(const ac::PaTables& t, ac::PaJobParams& jp, std
       jb.x = (ka - kc0) * 66 * 4;                      // byte offset of the first row of T (66 words per row)
       jb.y = static_cast<int>(mma_w4.size()) * 8;      // byte offset of the weights, each stored twice (packed pairs)
       jb.z = steps;
-      // byte offset of P[band][0] (64 items per band) with the XOR swizzle of the band folded in (the kernel xors
-      // 8 * lane: a lane owns the item pair 2 lane, 2 lane + 1)
-      // bits 18 ..: the same row in the operand layout of the tcgen05 product (psycho_mma_kernels.cu, tc_desc): band i at
-      // position kp = i ^ 4, atoms of four bands 512 bytes apart, 128 bytes per band, 32-byte chunks XORed with kp & 3
+      // low 16 bits: byte offset of the band's row of P in the operand layout of the tcgen05 product (psycho_mma_kernels.cu,
+      // tc_desc): band i at position kp = i ^ 4, atoms of four bands 512 bytes apart, 128 bytes per band, 32-byte chunks
+      // XORed with kp & 3 (the kernel xors the lane's part: a lane owns the item pair 2 lane, 2 lane + 1).  Bits 18 ..: byte
+      // offset of P[band][0] in the layout of the mma.sync product (64 items per band, XOR swizzle of the band folded in)
       const int kp = i ^ 4;
-      const int tc_off = (kp >> 2) * 512 + (kp & 3) * 128 + ((kp & 3) << 5);
-      jb.w = (i * 256 + ((i & 3) << 5)) | (partial ? 0x10000 : 0) | (final ? 0x20000 : 0) | (tc_off << 18);
+      const unsigned tc_off = static_cast<unsigned>((kp >> 2) * 512 + (kp & 3) * 128 + ((kp & 3) << 5));
+      const unsigned sync_off = static_cast<unsigned>(i * 256 + ((i & 3) << 5));
+      jb.w = static_cast<int>(tc_off | (partial ? 0x10000u : 0u) | (final ? 0x20000u : 0u) | (sync_off << 18));
       for (int k = ka; k < ka + 4 * steps; ++k)
         mma_w4.push_back(k < kb ? t.band_w[t.band_ptr[i] + (k - t.band_k0[i])] : 0.f);
       job_desc.push_back(jb);

@@ -49,6 +49,7 @@ constexpr int kTS = 66;       // row stride of T (words): 8-byte aligned item pa
 constexpr int kGS = 68;       // row stride of G: conflict-free stores from the accumulator layout (8 t + g), 16-byte rows
 constexpr int kPS = 64;       // row stride of P
 constexpr int kNB = 64;       // bark bands
+constexpr int kChunk = 64;    // filters per chunk of T (the job lists are built for it: capi.cu, build_mma_jobs)
 
 template <int C> struct Vec;
 template <> struct Vec<1> { using F = float; using I = int32_t; };
@@ -168,14 +169,14 @@ constexpr int kTcIssuer = 64;         // the thread that issues the product: lan
 
 // fused: the single-pass encoder (x -> q): T holds ALL filters of the tile's frames (the forward MDCT leaves them
 // there, transposed) instead of two chunk buffers
-__host__ __device__ inline Layout2 layout2(const PaDeviceTables& tb, const bool fused = false, const bool tc = false) {
+// n_fix: filters_n as a compile-time constant of the calling kernel (0: tb.n)
+__host__ __device__ inline Layout2 layout2(const PaDeviceTables& tb, const bool fused = false, const bool tc = false,
+                                           const int n_fix = 0) {
   Layout2 L;
-  const int kc = tb.n < tb.mma_chunk_k ? tb.n : tb.mma_chunk_k;
-  const int t_rows = ((fused ? tb.n : kc) + 3) * kTS;   // 3 zero rows behind the chunk for the 4-filter steps
+  const int n = n_fix > 0 ? n_fix : tb.n;
+  const int kc = n < kChunk ? n : kChunk;
+  const int t_rows = ((fused ? n : kc) + 3) * kTS;      // 3 zero rows behind the chunk for the 4-filter steps
   int o = 0;
-  const int pow_words = pow_tables_needed(tb) ? 512 : 0;
-  L.powa = o;    o += pow_words;                        // the exponent tables come first: an index with the sign bit
-  L.powia = o;   o += pow_words;                        //   set (NaN input) still reads inside the allocation
   L.tbuf = tc ? (t_rows + 255) & ~255 : (t_rows + 3) & ~3;
   L.t = o;       o += (fused ? 1 : 2) * L.tbuf;         // two chunk buffers: one is filled while the other is read
   // G [64][kGS] aliases P and the tonality partials behind it: both are dead once the MMA loop and the per-item
@@ -188,18 +189,23 @@ __host__ __device__ inline Layout2 layout2(const PaDeviceTables& tb, const bool 
   L.sfl = o;     o += tc ? kTcTable : 128;
   L.quiet = o;   o += kNB;
   L.lin = o;     o += kNB;
-  L.bw8 = o;     o += (2 * tb.n_mma_w4 + 3) & ~3;        // every weight twice: a packed pair for both items of a lane
-  L.filt4 = o;   o += filt_in_smem(tb) ? 4 * tb.n : 0;   // long filter tables stay in global memory (L1 / L2)
   // mbarrier of the tcgen05 product (8 bytes), tensor-memory address, mbarrier of the fused encoder's bulk copy, the two
   // ticket slots of the tile scheduler: no static shared memory, so the dynamic window starts 1024-byte aligned
   L.misc = o;    o += 12;
+  L.bw8 = o;     o += (2 * tb.n_mma_w4 + 3) & ~3;        // every weight twice: a packed pair for both items of a lane
+  L.filt4 = o;   o += filt_in_smem(tb) ? 4 * n : 0;      // long filter tables stay in global memory (L1 / L2)
+  // the exponent tables come last (every offset above is a compile-time constant when filters_n is): 256 entries each,
+  // and 256 more words so that an index with the sign bit set (NaN input) still reads inside the allocation
+  const int pow_words = pow_tables_needed(tb) ? 512 : 0;
+  L.powa = o;    o += pow_words;
+  L.powia = o;   o += pow_words + (pow_words ? 512 : 0);
   L.total = o;
   return L;
 }
 
 // the tensor-memory port needs a dead chunk buffer that holds the 16 KB low-order term of P
 __host__ __device__ inline bool tc_layout_ok(const PaDeviceTables& tb) {
-  return layout2(tb, false, true).tbuf >= kNB * kTI && tb.mma_n_chunks >= 2;
+  return tb.mma_chunk_k == kChunk && layout2(tb, false, true).tbuf >= kNB * kTI && tb.mma_n_chunks >= 2;
 }
 
 // asynchronous global -> shared copies of 4 or 8 bytes (LDGSTS): the destination address is free, so the copy
@@ -605,8 +611,8 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   static_assert(FT % kWarps == 0, "tile shape");
   static_assert(!FUSED || (C == 2 && NFIX == 256), "the fused encoder is built for stereo, filters_n = 256");
   extern __shared__ __align__(1024) float sm[];  // TC: P and the chunk buffers are swizzled operand tiles (1024-byte atoms)
-  const Layout2 L = layout2(tb, FUSED, TC);
-  const int n = NFIX > 0 ? NFIX : tb.n, kc = n < tb.mma_chunk_k ? n : tb.mma_chunk_k;
+  const Layout2 L = layout2(tb, FUSED, TC, NFIX);
+  const int n = NFIX > 0 ? NFIX : tb.n, kc = n < kChunk ? n : kChunk;
   const int n_chunks = tb.mma_n_chunks;
   float2* s_powa = reinterpret_cast<float2*>(sm + L.powa);
   float2* s_powia = reinterpret_cast<float2*>(sm + L.powia);
@@ -744,7 +750,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   // (their results are never stored).  The three rows behind the chunk are zeroed for the 4-filter steps.
   auto load_chunk = [&](int64_t f0, int nf, int chunk, int buf) {
     if (ablate & 32) return;
-    const int kc0 = chunk * tb.mma_chunk_k;
+    const int kc0 = chunk * kChunk;
     const int kcn = (n - kc0 < kc ? n - kc0 : kc);
     if (kcn != kc) {                            // a short last chunk: its zero rows sit inside the data rows of the others
       float* tz = sm + L.t + buf * L.tbuf + kcn * TS;
@@ -930,7 +936,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
           load_chunk(nf0, static_cast<int>(frames_total - nf0 < FT ? frames_total - nf0 : FT), 0, par ^ 1);
         }
       }
-      const uint32_t t_lane = FUSED ? t_base + static_cast<uint32_t>(chunk * tb.mma_chunk_k) * (TS * 4u) + static_cast<uint32_t>(lane) * 8u
+      const uint32_t t_lane = FUSED ? t_base + static_cast<uint32_t>(chunk * kChunk) * (TS * 4u) + static_cast<uint32_t>(lane) * 8u
                                     : t_base + static_cast<uint32_t>(par) * tbuf_bytes + static_cast<uint32_t>(lane) * 8u;
 
       // ---- A1: tonality sums over this warp's share of the filters: sum I and sum log2 max(eps, I)   (:113, :312)
@@ -1013,9 +1019,10 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
             a1 = ffma2(fmul2(y3, y3), w3, a1);
           }
           u64 acc2 = fadd2(a0, a1);
-          // TC: the operand layout of tc_desc (bits 18.. of the descriptor word; lanes 16 - 31 own items 32 - 63)
-          const uint32_t pp = TC ? p_base + ((static_cast<uint32_t>(jb.w) >> 18) ^ tc_lane_off)
-                                 : p_base + ((static_cast<uint32_t>(jb.w) & 0xffffu) ^ (static_cast<uint32_t>(lane) << 3));
+          // TC: the operand layout of tc_desc (low 16 bits of the descriptor word; lanes 16 - 31 own items 32 - 63);
+          // mma.sync: [band][item ^ swizzle] (bits 18 ..)
+          const uint32_t pp = TC ? p_base + ((static_cast<uint32_t>(jb.w) & 0xffffu) ^ tc_lane_off)
+                                 : p_base + ((static_cast<uint32_t>(jb.w) >> 18) ^ (static_cast<uint32_t>(lane) << 3));
           if (jb.w & 0x10000) acc2 = fadd2(acc2, lds_b64<0>(pp));
           if (jb.w & 0x20000) {
             float ax, ay;
@@ -1646,7 +1653,7 @@ cudaError_t pa_encode_fused(const PaDeviceTables& tb_in, const MdctDeviceTables&
 }
 
 bool pa_mma_tile_supported(const PaDeviceTables& tb, int channels) {
-  if (!tb.tile_ok || tb.nb != kNB || tb.jobs_host == nullptr) return false;
+  if (!tb.tile_ok || tb.nb != kNB || tb.jobs_host == nullptr || tb.mma_chunk_k != kChunk) return false;
   if (!(channels == 1 || channels == 2 || channels == 4)) return false;
   return static_cast<size_t>(layout2(tb).total) * sizeof(float) <= 200 * 1024;
 }

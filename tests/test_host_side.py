@@ -166,10 +166,11 @@ def test_mma_job_list_reproduces_w(sr, n):
     assert t[0] == 0 and t[8] == kcn and list(t) == sorted(t)
     for j in range(start[9 * c], start[9 * c + 8]):
       x, y, steps, wd = (int(v) for v in jobs[4 * j:4 * j + 4])
-      band, swz = (wd & 0xffff) // 256, ((wd & 0xffff) % 256) // 4
+      so = (wd & 0xffffffff) >> 18                             # row of P in the layout of the mma.sync product
+      band, swz = so // 256, (so % 256) // 4
       assert swz == (band & 3) << 3 and x % 264 == 0 and y % 32 == 0 and steps >= 1
-      kp = band ^ 4                                            # the same row in the tcgen05 operand layout (bits 18 ..)
-      assert (wd >> 18) == (kp >> 2) * 512 + (kp & 3) * 128 + ((kp & 3) << 5) and wd > 0
+      kp = band ^ 4                                            # the same row in the tcgen05 operand layout (low 16 bits)
+      assert (wd & 0xffff) == (kp >> 2) * 512 + (kp & 3) * 128 + ((kp & 3) << 5)
       row0 = x // 264
       assert row0 + 4 * steps <= kcn + 3                       # padded steps stay inside the three zero rows
       assert bool(wd & 0x10000) == (band in seen_band)         # an earlier chunk holds the first part of the band
