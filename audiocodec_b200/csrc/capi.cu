@@ -1034,28 +1034,66 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
     if (err == cudaSuccess) err = e;
     return err == cudaSuccess;
   };
-  // chunk schedule: small chunks at both ends (1, 1, 2, 4, ... clips up to chunk_clips and down again) keep the
-  // fill (first H2D + kernels before the first D2H can start) and the drain (last kernels + D2H) of the pipeline
-  // short; the middle runs at the full chunk size
+  // chunk schedule: the D2H copy of a chunk can only start when its H2D copy and its kernels are over, so the D2H stream
+  // trails the H2D stream by one chunk, idles whenever the chunks grow, and the call ends one (last) chunk after the last
+  // H2D copy.  A linear ramp (1, 2, ..., 8) / 8 of chunk_clips at the start (the first D2H starts after one clip, every growth step
+  // costs one clip of idle D2H), full chunks in the middle, a ramp down in steps of two at the end: measured best of
+  // fifteen schedules on cfg2 (tools/e2e_schedules.py: 5.25 ms against 5.45 for the doubling ramp, 5.45 for uniform chunks)
   std::vector<int64_t> chunk_of;
   {
-    std::vector<int64_t> head, tail;
-    int64_t left = batches, next = 1;
-    bool first = true;
-    while (left > 0) {
-      int64_t h = std::min(std::min(next, p->chunk_clips), left);
-      head.push_back(h);
-      left -= h;
-      if (left > 0) {
-        int64_t t = std::min(std::min(next, p->chunk_clips), left);
-        tail.push_back(t);
-        left -= t;
-      }
-      if (!first && next < p->chunk_clips) next *= 2;    // saturates: a long batch runs this loop thousands of times
-      first = false;
+    const int64_t S = p->chunk_clips, step = std::max<int64_t>(1, S / 8);     // eight ramp steps whatever the clip length
+    std::vector<int64_t> up, down;
+    int64_t up_sum = 0, down_sum = 0;
+    for (int64_t v = step; v < S; v += step) {
+      up.push_back(v);
+      up_sum += v;
     }
-    chunk_of = head;
-    chunk_of.insert(chunk_of.end(), tail.rbegin(), tail.rend());
+    for (int64_t v = S - 2 * step; v >= step; v -= 2 * step) {
+      down.push_back(v);
+      down_sum += v;
+    }
+    int64_t left = batches;
+    if (left <= up_sum + down_sum) {        // a short batch: as much of the ramp up as fits, the rest in one piece
+      for (int64_t v : up) {
+        if (left <= 0) break;
+        const int64_t take = std::min(v, left);
+        chunk_of.push_back(take);
+        left -= take;
+      }
+      while (left > 0) {
+        const int64_t take = std::min(S, left);
+        chunk_of.push_back(take);
+        left -= take;
+      }
+    } else {
+      chunk_of = up;
+      left -= up_sum + down_sum;
+      while (left > 0) {
+        const int64_t take = std::min(S, left);
+        chunk_of.push_back(take);
+        left -= take;
+      }
+      chunk_of.insert(chunk_of.end(), down.begin(), down.end());
+    }
+    // AC_PIPE_SCHEDULE="c0,c1,..." (development): explicit chunk sizes, the last one repeated, each at most chunk_clips
+    if (const char* e = std::getenv("AC_PIPE_SCHEDULE")) {
+      std::vector<int64_t> forced;
+      int64_t rest = batches, last = 1;
+      const char* q = e;
+      while (rest > 0) {
+        if (*q) {
+          char* end = nullptr;
+          const long v = std::strtol(q, &end, 10);
+          if (end == q) break;
+          last = std::max<int64_t>(1, std::min<int64_t>(v, p->chunk_clips));
+          q = (*end == ',') ? end + 1 : end;
+        }
+        const int64_t take = std::min(last, rest);
+        forced.push_back(take);
+        rest -= take;
+      }
+      if (rest == 0 && !forced.empty()) chunk_of = forced;
+    }
   }
   const size_t n_chunks = chunk_of.size();
   cudaStream_t caller = static_cast<cudaStream_t>(stream);
@@ -1065,30 +1103,52 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
   ok(cudaStreamWaitEvent(p->d2h, p->entry, 0));
   if (stats != nullptr) ok(cudaMemsetAsync(p->stats_dev, 0, 3 * sizeof(unsigned long long), p->run));
   // Per chunk k (slot k mod K), enqueued in this order so that every event is recorded before it is waited for:
-  //   h2d: wait until the forward MDCT of chunk k - K has read the slot's x      -> copy x      -> x_ready
-  //   run: wait for x_ready and until x_hat of chunk k - K has left the slot     -> four kernels -> x_free, out_ready
-  //   d2h: wait for out_ready                                                    -> copy x_hat   -> out_free
-  // The host thread runs ahead of the GPU, so the copy engines see up to K chunks of work queued behind the kernels.
+  //   host: until the forward MDCT of chunk k - K has read the slot's x and x_hat of chunk k - K has left the slot
+  //   h2d:  copy x -> x_ready
+  //   run:  wait for x_ready -> the kernels -> x_free, out_ready
+  //   d2h:  wait for out_ready -> copy x_hat -> out_free
+  // The re-use of a ring slot is gated on the HOST (cudaEventSynchronize), not by a stream wait: a cross-stream wait in
+  // front of a copy measured ~45 us of idle copy engine per chunk even when its event had long completed (B200,
+  // tools/e2e_trace.py), the host gate costs nothing because the streams still hold K - 1 chunks of queued work.
+  // AC_PIPE_TRACE=1 (development): timing events around every stage of every chunk, printed relative to the entry
+  std::vector<cudaEvent_t> tr;
+  const bool trace = std::getenv("AC_PIPE_TRACE") != nullptr;
+  auto mark = [&](cudaStream_t st) {
+    if (!trace) return;
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, st);
+    tr.push_back(e);
+  };
+  mark(p->h2d);
   size_t k = 0;
   for (int64_t i = 0; k < n_chunks && err == cudaSuccess; i += chunk_of[k], ++k) {
     const int64_t cb = chunk_of[k];
     const int slot = static_cast<int>(k % K);
     float* xs = p->x_ring + slot * in_slot;
     float* xh = p->xhat_ring + slot * out_slot;
-    if (k >= K) ok(cudaStreamWaitEvent(p->h2d, p->x_free[slot], 0));
+    if (k >= K) {
+      ok(cudaEventSynchronize(p->x_free[slot]));
+      ok(cudaEventSynchronize(p->out_free[slot]));
+    }
+    mark(p->h2d);
     if (in_clip > 0)
       ok(cudaMemcpyAsync(xs, x_host + i * in_clip, cb * in_clip * sizeof(float), cudaMemcpyHostToDevice, p->h2d));
+    mark(p->h2d);
     ok(cudaEventRecord(p->x_ready[slot], p->h2d));
     ok(cudaStreamWaitEvent(p->run, p->x_ready[slot], 0));
-    if (k >= K) ok(cudaStreamWaitEvent(p->run, p->out_free[slot], 0));
+    mark(p->run);
     ok(ac::mdct_forward(p->mdct->tb, xs, p->y, cb, blocks, c, p->run));
     ok(cudaEventRecord(p->x_free[slot], p->run));
     ok(ac::pa_threshold(p->pa->tb, p->y, nullptr, drown, thr_scale, p->step, p->q, cb * frames, c, p->run));
     if (stats != nullptr) ok(ac::codec_stats(p->q, cb * frames * n * c, p->stats_dev, p->run));
     ok(ac::mdct_inverse(p->mdct->tb, nullptr, p->q, p->step, xh, cb, frames, c, p->run));
+    mark(p->run);
     ok(cudaEventRecord(p->out_ready[slot], p->run));
     ok(cudaStreamWaitEvent(p->d2h, p->out_ready[slot], 0));
+    mark(p->d2h);
     ok(cudaMemcpyAsync(xhat_host + i * out_clip, xh, cb * out_clip * sizeof(float), cudaMemcpyDeviceToHost, p->d2h));
+    mark(p->d2h);
     ok(cudaEventRecord(p->out_free[slot], p->d2h));
   }
   unsigned long long host_stats[3] = {0, 0, 0};
@@ -1100,6 +1160,17 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
   ok(cudaEventRecord(p->done, p->d2h));
   ok(cudaStreamWaitEvent(caller, p->done, 0));
   ok(cudaEventSynchronize(p->done));          // the result is host memory: hand it back complete
+  if (trace) {
+    cudaDeviceSynchronize();
+    std::fprintf(stderr, "chunk clips | h2d start end | kernels start end | d2h start end   (us after the first H2D was enqueued)\n");
+    for (size_t j = 0; j < n_chunks && 1 + 6 * j + 5 < tr.size(); ++j) {
+      float t[6];
+      for (int u = 0; u < 6; ++u) cudaEventElapsedTime(&t[u], tr[0], tr[1 + 6 * j + u]);
+      std::fprintf(stderr, "%3zu %3lld | %8.1f %8.1f | %8.1f %8.1f | %8.1f %8.1f\n", j, (long long)chunk_of[j], 1e3 * t[0], 1e3 * t[1],
+                   1e3 * t[2], 1e3 * t[3], 1e3 * t[4], 1e3 * t[5]);
+    }
+    for (cudaEvent_t e : tr) cudaEventDestroy(e);
+  }
   if (err != cudaSuccess) return cuda_fail(err, "streaming round trip");
   if (stats != nullptr) {
     stats[0] = static_cast<double>(host_stats[0]);
