@@ -1103,16 +1103,16 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
   ok(cudaStreamWaitEvent(p->d2h, p->entry, 0));
   if (stats != nullptr) ok(cudaMemsetAsync(p->stats_dev, 0, 3 * sizeof(unsigned long long), p->run));
   // Per chunk k (slot k mod K), enqueued in this order so that every event is recorded before it is waited for:
-  //   host: until the forward MDCT of chunk k - K has read the slot's x and x_hat of chunk k - K has left the slot
-  //   h2d:  copy x -> x_ready
-  //   run:  wait for x_ready -> the kernels -> x_free, out_ready
-  //   d2h:  wait for out_ready -> copy x_hat -> out_free
-  // The re-use of a ring slot is gated on the HOST (cudaEventSynchronize), not by a stream wait: a cross-stream wait in
-  // front of a copy measured ~45 us of idle copy engine per chunk even when its event had long completed (B200,
-  // tools/e2e_trace.py), the host gate costs nothing because the streams still hold K - 1 chunks of queued work.
+  //   h2d: wait until the forward MDCT of chunk k - K has read the slot's x      -> copy x      -> x_ready
+  //   run: wait for x_ready and until x_hat of chunk k - K has left the slot     -> the kernels -> x_free, out_ready
+  //   d2h: wait for out_ready                                                    -> copy x_hat   -> out_free
+  // The host thread runs ahead of the GPU, so the copy engines see up to K chunks of work queued behind the kernels.
+  // (AC_PIPE_HOST_GATE gates the re-use of a ring slot with cudaEventSynchronize on the host instead of the two stream
+  // waits: measured equal on B200, tools/e2e_schedules.py.)
   // AC_PIPE_TRACE=1 (development): timing events around every stage of every chunk, printed relative to the entry
   std::vector<cudaEvent_t> tr;
   const bool trace = std::getenv("AC_PIPE_TRACE") != nullptr;
+  const bool stream_gate = std::getenv("AC_PIPE_HOST_GATE") == nullptr;     // development: A/B of the two gates
   auto mark = [&](cudaStream_t st) {
     if (!trace) return;
     cudaEvent_t e = nullptr;
@@ -1128,8 +1128,13 @@ int ac_codec_roundtrip_host_f32(ac_codec_pipeline* p, const float* x_host, float
     float* xs = p->x_ring + slot * in_slot;
     float* xh = p->xhat_ring + slot * out_slot;
     if (k >= K) {
-      ok(cudaEventSynchronize(p->x_free[slot]));
-      ok(cudaEventSynchronize(p->out_free[slot]));
+      if (stream_gate) {
+        ok(cudaStreamWaitEvent(p->h2d, p->x_free[slot], 0));
+        ok(cudaStreamWaitEvent(p->run, p->out_free[slot], 0));
+      } else {
+        ok(cudaEventSynchronize(p->x_free[slot]));
+        ok(cudaEventSynchronize(p->out_free[slot]));
+      }
     }
     mark(p->h2d);
     if (in_clip > 0)

@@ -1,4 +1,5 @@
-"""Development aid: AudioCodec.roundtrip_host on cfg2 (pinned buffers) for explicit chunk schedules (AC_PIPE_SCHEDULE)."""
+"""Development aid: AudioCodec.roundtrip_host on cfg2 (pinned buffers) for explicit chunk schedules (AC_PIPE_SCHEDULE)
+and for the two ways of gating the re-use of a ring slot (AC_PIPE_HOST_GATE), interleaved in one process."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,19 +11,26 @@ x = (torch.rand(b, s, c) - 0.5).pin_memory()
 out = torch.empty(b, s + 2 * n, c).pin_memory()
 
 
-def timeit(reps=8):
-  codec.roundtrip_host(x, out, chunk_clips=16); torch.cuda.synchronize()
+def timeit(reps=10):
+  codec.roundtrip_host(x, out, chunk_clips=8); torch.cuda.synchronize()
   t0 = time.perf_counter()
   for _ in range(reps):
-    codec.roundtrip_host(x, out, chunk_clips=16)
+    codec.roundtrip_host(x, out, chunk_clips=8)
   torch.cuda.synchronize()
   return (time.perf_counter() - t0) / reps * 1e3
 
 
-schedules = ["1,1,2,4,8,8,8,8,8,8,4,2,1,1", "2,2,4,4", "1,2,4,4", "1,2,3,4,5,6,7,8,8,8,6,4,2", "16", "6", "8", "1,1,2,4,8", "1,2,4,8,8,8,8,8,8,8,4",
-             "1,2,4,6,6,6,6,6,6,6,6,6,2,1", "2,4,8,8,8,8,8,8,6,3,1", "1,1,2,4,8,8,8,8,8,8,5,2,1", "3,5,8,8,8,8,8,8,5,3", "1,1,2,4,8,16,16,8,4,2,1,1",
-             "1,1,2,4,5,5,5,5,5,5,5,5,5,5,5,2"]
-for rep in range(2):
-  for sch in schedules:
-    os.environ["AC_PIPE_SCHEDULE"] = sch
-    print(f"{sch:45s} {timeit():.2f} ms")
+schedules = {"doubling": "1,1,2,4,8,8,8,8,8,8,4,2,1,1", "linear": "1,2,3,4,5,6,7,8,8,8,6,4,2", "linear from 2": "2,3,4,5,6,7,8,8,8,7,4,2",
+             "uniform 8": "8"}
+res = {}
+for rep in range(4):
+  for name, sch in schedules.items():
+    for gate in ("host", "stream"):
+      os.environ["AC_PIPE_SCHEDULE"] = sch
+      if gate == "host":
+        os.environ["AC_PIPE_HOST_GATE"] = "1"
+      else:
+        os.environ.pop("AC_PIPE_HOST_GATE", None)
+      res.setdefault((name, gate), []).append(timeit())
+for k, v in res.items():
+  print(f"{k[0]:14s} {k[1]:6s} gate: " + " ".join(f"{t:.2f}" for t in v) + f"   min {min(v):.2f} ms")
