@@ -364,7 +364,7 @@ def cfg5_sweep(torch, dist, device, rank, world, barrier):
           "chain_gbs_per_gpu": alg / world / (ms * 1e-3) / 1e9}
 
 
-def run_b200_arm(args):
+def run_b200_arm(args, stdout_fd=1):
   import torch
   import torch.distributed as dist
 
@@ -531,7 +531,8 @@ def run_b200_arm(args):
         os.sched_setaffinity(0, _ORIGINAL_AFFINITY)      # the CPU port gets every host core again
       v, info = cpu_port_throughput(args.workload, budget_s=20.0, steps=2, warmup=1)
       line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": info["sample"]}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(stdout_fd, (json.dumps(line) + "\n").encode())
   if world > 1:
     dist.destroy_process_group()
   return 0
@@ -603,7 +604,17 @@ def main():
   args = ap.parse_args()
   if args.impl == "reference":
     return run_reference_arm(args)
-  return run_b200_arm(args)
+  # stdout carries exactly ONE line, the JSON: NCCL prints its version banner to file descriptor 1 from C when the first
+  # communicator comes up, so everything before the final print goes to stderr
+  sys.stdout.flush()
+  saved = os.dup(1)
+  os.dup2(2, 1)
+  try:
+    return run_b200_arm(args, stdout_fd=saved)
+  finally:
+    sys.stdout.flush()
+    os.dup2(saved, 1)
+    os.close(saved)
 
 
 if __name__ == "__main__":
