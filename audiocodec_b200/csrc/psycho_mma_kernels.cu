@@ -833,7 +833,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
       }
     }
   };
-  pdl_launch_dependents();                      // the next kernel on the stream may start its prologue
+  if (!(ablate & 128)) pdl_launch_dependents(); // the next kernel on the stream may start its prologue (128: experiment, at the end)
   pdl_wait();                                   // the producer of y (x) has completed; the tables above are plan constants
   if (tile_i < tiles) {
     if constexpr (FUSED) {
@@ -1432,6 +1432,7 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
     tpar ^= 1;
     ++slot_i;
   }
+  if (ablate & 128) pdl_launch_dependents();
   if (tid == 0 && atomicAdd(sched + 1, 1u) == gridDim.x - 1) {   // every CTA has drawn its last ticket
     sched[0] = 0u;
     sched[1] = 0u;
