@@ -1,5 +1,5 @@
 // Psychoacoustic tile kernel, second generation (sm_100a): global masking threshold + fused quantiser with the
-// 64 x 64 spreading contraction on the tensor cores.
+// 64 x 64 spreading contraction on the 5th-generation tensor cores (tcgen05.mma, accumulator in tensor memory).
 //
 // Reference behaviour: /root/reference/audiocodec/psychoacoustic.py:102-120 (tonality), :122-148
 // (global_masking_threshold), :169-210 (_masking_intensity_in_bark), :301-331 (bark mappings); quantiser = SURVEY.md
@@ -13,14 +13,18 @@
 //                           dealt to the warps so that they level the band-sum jobs (PaJobParams::ton_start)
 //   A2  lane <-> item pair  one job per (bark band, chunk): steps of four filters (LDS.64, square, FFMA2 per filter and
 //                           item pair); the job list is a by-value kernel parameter = constant bank = warp-uniform
-//                           control; P = max(eps, I_bark)^alpha through an exponent table (x^a = 2^(a lg2 mantissa +
-//                           r[E]) * 2^n[E]: no int <-> float conversions, the exponent keeps fp32 precision), P stored
-//                           XOR-swizzled
-//   B   mma.sync m16n8k8    acc[item][j] = sum_i P[item][i] S[i][j] as an error-compensated TF32 product
-//                           (P = hi + lo, S = hi + lo, three MMAs: lo hi + hi lo + hi hi; every term is positive, the
-//                           dropped lo lo term is 2^-22 relative) with fp32 accumulators: 16 items x 32 bands per warp.
-//                           The Toeplitz S is read from two 128-entry tables; fragment (k-step, n-tile) only depends
-//                           on n-tile - k-step, so one new fragment per k-step is loaded and the rest rotate.
+//                           control; P = max(eps, I_bark)^alpha as sqrt(x) x^(alpha - 1/2) (alpha near 1/2; else through
+//                           an exponent table: x^a = 2^(a lg2 mantissa + r[E]) * 2^n[E]), stored straight into the
+//                           operand layout of the product (the job descriptor carries the band's row)
+//   B   tcgen05.mma         acc[item][j] = sum_i P[item][i] S[i][j] as an error-compensated TF32 product (P = hi + lo,
+//       kind::tf32          S = hi + lo: hi lo + hi hi + lo hi; every term is positive, the dropped lo lo term is 2^-22
+//       M 64, N 64, K 8     relative) with the fp32 accumulator in tensor memory: 24 single-thread instructions per tile.
+//                           A = P in place (MN-major, SWIZZLE_128B_BASE32B; the unsplit value is the high-order term, the
+//                           low-order term goes to the dead chunk buffer), B = the Toeplitz S as a table of 30 K-major core
+//                           matrices addressed as overlapping windows; tcgen05.ld.16x256b returns the accumulator in the
+//                           mma.sync fragment layout (see tc_desc below).  mma.sync m16n8k8 form of the same product
+//                           (fragments from two 128-entry tables, rotated in registers) for plans whose operand layout
+//                           would cost a resident CTA and under AC_PA_MMA=sync.
 //       epilogue            in the accumulator layout: the masking offset joins the exponent of ^(1/alpha)
 //                           (10^(-alpha offset / 10))^(1/alpha) = 2^(offset_log2 offset)), quiet threshold, scale^2
 //   D   lane <-> filter k   thr = sqrt(sum_b G[b] W_inv[b][k]) as v * rsqrt(v); the same rsqrt seeds the division
