@@ -154,6 +154,12 @@ int unwrap_dl(struct DLManagedTensor* m, const char* name, int ndim, uint8_t cod
 
 }  // namespace
 
+static int __float_as_int_host(float f) {
+  int i;
+  std::memcpy(&i, &f, sizeof(i));
+  return i;
+}
+
 // Band-sum job list of the tensor-core tile kernel (psycho_mma_kernels.cu; PaJobParams in kernels.h): chunks of 64
 // filters, one job per (band, chunk) = steps of four filters with zero-padded weights; the jobs of a chunk are dealt
 // to the eight warps in contiguous runs of equal cost, and the filters of the chunk's tonality pass in contiguous runs
@@ -706,6 +712,15 @@ int ac_pa_plan_create_ex(double sample_rate, int filter_bands_n, int bark_bands_
         for (int sl = 0; sl < 3; ++sl)
           if (w3[sl] != 0.f) d.filt_mask[k / 32] |= static_cast<uint8_t>(1u << sl);
     }
+    float floor_min = INFINITY;      // the quiet threshold's share of every filter's intensity threshold, as the kernel sums it
+    for (int k = 0; k < t.n; ++k) {
+      const int b0 = __float_as_int_host(filt4[k].w);
+      float v = 0.f;
+      const float w3[3] = {filt4[k].x, filt4[k].y, filt4[k].z};
+      for (int sl = 0; sl < 3; ++sl) v += w3[sl] * static_cast<float>(t.quiet[b0 + sl]);
+      floor_min = std::min(floor_min, v);
+    }
+    d.thr_clamp_needed = (floor_min >= 4.0f * d.eps) ? 0 : 1;
   }
   std::vector<float> quiet(t.quiet.begin(), t.quiet.end()), spread(t.spread_fn.begin(), t.spread_fn.end());
   if ((err = upload(t.band_k0, &d.band_k0, plan->owned)) != cudaSuccess ||

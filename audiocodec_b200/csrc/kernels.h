@@ -98,6 +98,9 @@ struct PaDeviceTables {
   // three bits per group of 32 filters: bit s set when a filter of the group has a non-zero filt4 weight for band slot s
   uint8_t filt_mask[64] = {};
   int clamp_needed = 1;     // 0: max(eps, .) before ^(1/alpha) can never win against the quiet threshold
+  // 0: max(eps, .) before the square root of the filter-domain threshold (psychoacoustic.py:330-331) can never act - every
+  // filter's share of the quiet threshold alone is above 4 eps (the bark-domain threshold is >= the quiet threshold)
+  int thr_clamp_needed = 1;
   const PaJobParams* jobs_host = nullptr;   // HOST pointer (owned by the plan); null when the list does not fit
   const float2* pow_alpha = nullptr;
   const float2* pow_inv_alpha = nullptr;

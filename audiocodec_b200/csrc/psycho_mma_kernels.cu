@@ -444,7 +444,8 @@ __device__ __forceinline__ void phase_d_unit_mono2(const float4* __restrict__ fi
 // further), and their dependency chains interleave: fewer shared-memory wavefronts and control instructions per
 // coefficient than one pair at a time.  row_stride in floats; yv[h][i] = the pair's two amplitudes of filter 32 i + lane.
 // GUARD: pair h is stored only when h < pairs_live (ragged last tile of the fused encoder).
-template <int C, bool QUANT, bool THR, bool FILT_SMEM, int KI, int R, bool GUARD = false>
+// CLAMP: max(eps, .) before the square root (false when the plan's quiet threshold keeps every filter above eps)
+template <int C, bool QUANT, bool THR, bool FILT_SMEM, int KI, int R, bool GUARD = false, bool CLAMP = true>
 __device__ __forceinline__ void phase_d_unit_pairs(const float4* __restrict__ filt4, const unsigned masks,
                                                     const float2 (&yv)[R][KI], float* __restrict__ t0,
                                                     int32_t* __restrict__ q0, const size_t row_stride, const float* gr,
@@ -481,8 +482,10 @@ __device__ __forceinline__ void phase_d_unit_pairs(const float4* __restrict__ fi
       if (GUARD && h >= pairs_live) break;
       float vx, vy;
       unpack2(v[h], vx, vy);
-      vx = fmaxf(eps_s2, vx);
-      vy = fmaxf(eps_s2, vy);
+      if constexpr (CLAMP) {
+        vx = fmaxf(eps_s2, vx);
+        vy = fmaxf(eps_s2, vy);
+      }
       const u64 r2 = pack2(rsqrt_approx(vx), rsqrt_approx(vy));
       const u64 th2 = fmul2(pack2(vx, vy), r2);
       if (QUANT) {
@@ -1357,13 +1360,17 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
               unsigned masks = 0;
 #pragma unroll
               for (int i = 0; i < K2; ++i) masks |= static_cast<unsigned>(tb.filt_mask[k0 / 32 + i]) << (3 * i);
-#define AC_PHASE_D(THR_, FS_)                                                                                            \
-  phase_d_unit_pairs<C, QUANT, THR_, FS_, K2, R, FUSED>((FS_ ? s_filt4 : tb.filt4) + k0 + lane, masks, yv, thr_out + off, \
-                                                        q_out + off, rs, gr, eps_s2, rows_live - r0)
-              if (filt_smem) {
-                if (thr) AC_PHASE_D(true, true); else AC_PHASE_D(false, true);
+#define AC_PHASE_D(THR_, FS_, CL_)                                                                                           \
+  phase_d_unit_pairs<C, QUANT, THR_, FS_, K2, R, FUSED, CL_>((FS_ ? s_filt4 : tb.filt4) + k0 + lane, masks, yv, thr_out + off, \
+                                                             q_out + off, rs, gr, eps_s2, rows_live - r0)
+              if (filt_smem && !tb.thr_clamp_needed) {      // the headline plans: no clamp, table in shared memory
+                if (thr) AC_PHASE_D(true, true, false); else AC_PHASE_D(false, true, false);
+              } else if (filt_smem) {
+                if (thr) AC_PHASE_D(true, true, true); else AC_PHASE_D(false, true, true);
+              } else if (!tb.thr_clamp_needed) {
+                if (thr) AC_PHASE_D(true, false, false); else AC_PHASE_D(false, false, false);
               } else {
-                if (thr) AC_PHASE_D(true, false); else AC_PHASE_D(false, false);
+                if (thr) AC_PHASE_D(true, false, true); else AC_PHASE_D(false, false, true);
               }
 #undef AC_PHASE_D
             }
