@@ -46,14 +46,32 @@ def build(force=False, verbose=False):
     with open(stamp) as f:
       if f.read().strip() == fp:
         return lib_path()
-  cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-I", os.path.join(PKG, "..", "include"), "-o", lib_path()] + [os.path.join(CSRC, s) for s in SOURCES]
-  proc = subprocess.run(cmd, capture_output=True, text=True)
-  if proc.returncode != 0:
-    sys.stderr.write(proc.stdout + proc.stderr)
-    raise RuntimeError("nvcc failed building " + LIBNAME)
+  # one nvcc per source, in parallel (the masking kernels alone take a minute), then one link step
+  import concurrent.futures
+  import tempfile
+  compile_flags = [f for f in NVCC_FLAGS if f != "--shared"] + (["-Xptxas", "-v"] if verbose else [])
+  log = []
+  with tempfile.TemporaryDirectory(prefix="audiocodec_b200_build_") as tmp:
+    def compile_one(src):
+      obj = os.path.join(tmp, os.path.splitext(src)[0] + ".o")
+      proc = subprocess.run([_nvcc()] + compile_flags + ["-I", os.path.join(PKG, "..", "include"), "-c", "-o", obj,
+                             os.path.join(CSRC, src)], capture_output=True, text=True)
+      return src, obj, proc
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as pool:
+      results = list(pool.map(compile_one, SOURCES))
+    for src, obj, proc in results:
+      log.append(proc.stdout + proc.stderr)
+      if proc.returncode != 0:
+        sys.stderr.write("".join(log))
+        raise RuntimeError("nvcc failed compiling " + src)
+    link = subprocess.run([_nvcc()] + NVCC_FLAGS + ["-o", lib_path()] + [obj for _, obj, _ in results],
+                          capture_output=True, text=True)
+    log.append(link.stdout + link.stderr)
+    if link.returncode != 0:
+      sys.stderr.write("".join(log))
+      raise RuntimeError("nvcc failed linking " + LIBNAME)
   if verbose:
-    sys.stderr.write(proc.stdout + proc.stderr)
+    sys.stderr.write("".join(log))
   with open(stamp, "w") as f:
     f.write(fp)
   return lib_path()
