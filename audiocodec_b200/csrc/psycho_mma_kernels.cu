@@ -842,6 +842,18 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   };
   if (!(ablate & 128)) pdl_launch_dependents(); // the next kernel on the stream may start its prologue (128: experiment, at the end)
   pdl_wait();                                   // the producer of y (x) has completed; the tables above are plan constants
+  if (ablate >> 8) {
+    // experiment (profiles/README.md, phase bunching): every CTA starts its first tile at its own offset inside a window of
+    // (ablate >> 8) microseconds, so that the grid does not walk through its phases in lockstep
+    const unsigned window_ns = static_cast<unsigned>(ablate >> 8) * 1000u;
+    const unsigned wait_ns = (blockIdx.x * 2654435761u >> 8) % window_ns;
+    unsigned long long t_start, t_now;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
+    do {
+      __nanosleep(200);
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
+    } while (t_now - t_start < wait_ns);
+  }
   if (tile_i < tiles) {
     if constexpr (FUSED) {
       if (tid == 0) issue_x_load(tile_i);
