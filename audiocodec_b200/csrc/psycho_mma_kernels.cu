@@ -218,6 +218,12 @@ template <int BYTES>
 __device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
 }
+// with an L2 eviction-priority hint (createpolicy): y is read again from L2 in phase D
+template <int BYTES>
+__device__ __forceinline__ void cp_async_hint(uint32_t dst, const void* src, uint64_t policy) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], %2, %3;" ::"r"(dst), "l"(src), "n"(BYTES), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -755,6 +761,10 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   // y[f0 .. f0 + FT)[kc0 .. kc0 + kcn) -> T[buffer][filter][item], asynchronously.  Warp w copies its ROWS frame rows,
   // lanes run along the filters (coalesced reads); frame rows behind the end of the tensor re-read the last frame
   // (their results are never stored).  The three rows behind the chunk are zeroed for the 4-filter steps.
+  // the copies of y ask L2 to keep their lines (evict_last) until phase D has re-read them (evict_first)
+  uint64_t l2_policy, l2_policy_first;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(l2_policy));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(l2_policy_first));
   auto load_chunk = [&](int64_t f0, int nf, int chunk, int buf) {
     if (ablate & 32) return;
     const int kc0 = chunk * kChunk;
@@ -773,11 +783,11 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
 #pragma unroll
         for (int kk = 0; kk < 64; kk += 32) {
           if constexpr (C == 1) {
-            cp_async<4>(dst + r * 4 + kk * (TS * 4), src + r * rs + kk);
+            cp_async_hint<4>(dst + r * 4 + kk * (TS * 4), src + r * rs + kk, l2_policy);
           } else {
 #pragma unroll
             for (int c2 = 0; c2 < C; c2 += 2)
-              cp_async<8>(dst + (r * C + c2) * 4 + kk * (TS * 4), src + r * rs + kk * C + c2);
+              cp_async_hint<8>(dst + (r * C + c2) * 4 + kk * (TS * 4), src + r * rs + kk * C + c2, l2_policy);
           }
         }
     } else if (nf == FT && kcn == 32) {         // whole tile, whole 32-filter chunk
@@ -842,18 +852,6 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
   };
   if (!(ablate & 128)) pdl_launch_dependents(); // the next kernel on the stream may start its prologue (128: experiment, at the end)
   pdl_wait();                                   // the producer of y (x) has completed; the tables above are plan constants
-  if (ablate >> 8) {
-    // experiment (profiles/README.md, phase bunching): every CTA starts its first tile at its own offset inside a window of
-    // (ablate >> 8) microseconds, so that the grid does not walk through its phases in lockstep
-    const unsigned window_ns = static_cast<unsigned>(ablate >> 8) * 1000u;
-    const unsigned wait_ns = (blockIdx.x * 2654435761u >> 8) % window_ns;
-    unsigned long long t_start, t_now;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_start));
-    do {
-      __nanosleep(200);
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_now));
-    } while (t_now - t_start < wait_ns);
-  }
   if (tile_i < tiles) {
     if constexpr (FUSED) {
       if (tid == 0) issue_x_load(tile_i);
@@ -1363,9 +1361,14 @@ pa_mma_tile_kernel(const __grid_constant__ PaDeviceTables tb, const __grid_const
 #pragma unroll
                   for (int i = 0; i < K2; ++i) {
                     if constexpr (C == 2) {
-                      yv[h][i] = __ldcg(reinterpret_cast<const float2*>(y + off + h * rs) + 32 * i);   // L2 only
+                      asm volatile("ld.global.cg.L2::cache_hint.v2.f32 {%0, %1}, [%2], %3;"     // L2 only, last use
+                                   : "=f"(yv[h][i].x), "=f"(yv[h][i].y)
+                                   : "l"(reinterpret_cast<const float2*>(y + off + h * rs) + 32 * i), "l"(l2_policy_first));
                     } else {
-                      yv[h][i] = make_float2(__ldcg(y + off + (2 * h) * rs + 32 * i), __ldcg(y + off + (2 * h + 1) * rs + 32 * i));
+                      asm volatile("ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;"
+                                   : "=f"(yv[h][i].x) : "l"(y + off + (2 * h) * rs + 32 * i), "l"(l2_policy_first));
+                      asm volatile("ld.global.cg.L2::cache_hint.f32 %0, [%1], %2;"
+                                   : "=f"(yv[h][i].y) : "l"(y + off + (2 * h + 1) * rs + 32 * i), "l"(l2_policy_first));
                     }
                   }
               }
